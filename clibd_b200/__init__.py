@@ -1,0 +1,29 @@
+"""clibd_b200 -- B200-native (sm_100a) implementation of the CLIBD data-parallel hot path.
+
+Host-side mirror of the reference interfaces for that path:
+
+    from clibd_b200 import ContrastiveLoss, ClipLoss            # bioscanclip/model/loss_func.py
+    from clibd_b200 import make_prediction, inference_and_print_result, \
+        top_k_micro_accuracy, top_k_macro_accuracy, find_closest_match   # bioscanclip/util/util.py
+
+Everything computes through the C ABI of include/clibd_b200.h (clibd_b200/lib/libclibd_b200.so,
+built by ``python -m clibd_b200._build``); there is no CPU or eager-PyTorch fallback.
+"""
+from .loss import ClipLoss, ContrastiveLoss, construct_label_metrix, gather_features, pair_weights  # noqa: F401
+from .retrieval import (  # noqa: F401
+    LEVELS,
+    All_TYPE_OF_FEATURES_OF_KEY,
+    All_TYPE_OF_FEATURES_OF_QUERY,
+    find_closest_match,
+    inference_and_print_result,
+    knn_search,
+    make_prediction,
+    top_k_macro_accuracy,
+    top_k_micro_accuracy,
+)
+
+__all__ = [
+    "ClipLoss", "ContrastiveLoss", "construct_label_metrix", "gather_features", "pair_weights",
+    "LEVELS", "All_TYPE_OF_FEATURES_OF_KEY", "All_TYPE_OF_FEATURES_OF_QUERY", "find_closest_match",
+    "inference_and_print_result", "knn_search", "make_prediction", "top_k_macro_accuracy", "top_k_micro_accuracy",
+]

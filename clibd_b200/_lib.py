@@ -1,0 +1,83 @@
+"""ctypes binding of include/clibd_b200.h.  There is NO fallback: if the CUDA library is
+missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+_c = ctypes
+_P = _c.c_void_p
+_I64 = _c.c_int64
+_INT = _c.c_int
+_F = _c.c_float
+
+DT_F32, DT_BF16, DT_F16, DT_F64 = 0, 1, 2, 3
+PATH_SIMT_F32, PATH_TC_BF16, PATH_TC_F16 = 0, 1, 2
+
+# name -> (restype, argtypes); must list every symbol include/clibd_b200.h declares
+SIGNATURES = {
+    "clibd_abi_version": (_INT, []),
+    "clibd_last_error": (_c.c_char_p, []),
+    "clibd_device_supported": (_INT, []),
+    "clibd_row_inv_norm": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
+    "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
+    "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P,
+                                        _P, _P]),
+    "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P, _P, _P]),
+    "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P]),
+    "clibd_knn_normalize": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
+    "clibd_knn_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
+    "clibd_knn_search": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P]),
+    "clibd_knn_merge": (_INT, [_P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
+    "clibd_topk_accuracy": (_INT, [_P, _I64, _INT, _P, _I64, _P, _P, _INT, _c.c_int32, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer) the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("CLIBD_B200_REBUILD"):
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.clibd_abi_version() != 1:
+        raise RuntimeError("clibd_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().clibd_last_error().decode()
+        if rc == 1:
+            raise ValueError("clibd_b200: " + msg)
+        raise RuntimeError("clibd_b200: " + msg)
+
+
+def ptr_array3(ptrs):
+    """host array of 3 device pointers (None -> NULL)"""
+    arr = (_P * 3)()
+    for i, p in enumerate(ptrs):
+        arr[i] = _P(p) if p else _P(None)
+    return arr
+
+
+def float_array3(vals):
+    arr = (_F * 3)()
+    for i, v in enumerate(vals):
+        arr[i] = float(v)
+    return arr

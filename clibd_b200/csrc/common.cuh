@@ -1,0 +1,98 @@
+// Shared host/device helpers for the clibd_b200 CUDA library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace clibd {
+
+// dtype codes of the C ABI (include/clibd_b200.h)
+enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+// compute paths
+enum : int { PATH_SIMT_F32 = 0, PATH_TC_BF16 = 1, PATH_TC_F16 = 2 };
+
+void set_error(const std::string& msg);
+
+#define CLIBD_CHECK_CUDA(expr)                                                                    \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::clibd::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                        \
+            return 2;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define CLIBD_REQUIRE(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            ::clibd::set_error(std::string("invalid argument: ") + (msg)); \
+            return 1;                                              \
+        }                                                          \
+    } while (0)
+
+#define CLIBD_KERNEL_CHECK() CLIBD_CHECK_CUDA(cudaGetLastError())
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, int64_t i) {
+    return p[i];
+}
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) {
+    return __bfloat162float(p[i]);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, int64_t i) {
+    return __half2float(p[i]);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, int64_t i, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, int64_t i, float v) {
+    p[i] = v;
+}
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) {
+    p[i] = __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ void store_from_float<__half>(__half* p, int64_t i, float v) {
+    p[i] = __float2half_rn(v);
+}
+
+// 16-bit operand conversion selected at run time (fmt: 1 = bf16, 0 = f16, matching the
+// tcgen05 instruction-descriptor format codes)
+__device__ __forceinline__ uint16_t to_operand16(float v, int fmt) {
+    return fmt ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+}
+__device__ __forceinline__ uint32_t pack2_operand16(float lo, float hi, int fmt) {
+    if (fmt) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace clibd

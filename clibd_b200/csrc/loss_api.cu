@@ -1,0 +1,274 @@
+// extern "C" entry points of the contrastive-loss path (see include/clibd_b200.h).
+#include <string>
+
+#include "../../include/clibd_b200.h"
+#include "common.cuh"
+#include "loss_plan.h"
+
+namespace clibd {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
+    LossPlan p;
+    p.N = N;
+    p.n = n;
+    p.d = d;
+    p.path = path;
+    p.dpad = round_up(d, 64);
+    p.npad = round_up(N, 8);
+    const bool tc = path != PATH_SIMT_F32;
+    if (tc) {
+        p.row_parts = ceil_div(N, FWD_BN);
+        p.col_parts = ceil_div(n, FWD_BM);
+        const int64_t ctas = ceil_div(n, BWD_BM) * ceil_div(p.dpad, BWD_DCH);
+        int64_t js = ceil_div(2 * 148, ctas > 0 ? ctas : 1);
+        const int64_t num_jt = ceil_div(N, BWD_BJ);
+        if (js > 8) js = 8;
+        if (js > num_jt) js = num_jt;
+        if (js < 1) js = 1;
+        p.jsplit = static_cast<int>(js);
+    } else {
+        p.row_parts = ceil_div(N, SIMT_T);
+        p.col_parts = ceil_div(n, SIMT_T);
+        p.jsplit = 1;
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    p.off_rep = take(sizeof(int32_t) * N);
+    p.off_cnt = take(sizeof(float) * N);
+    p.off_gscale = take(sizeof(float) * 4);
+    for (int m = 0; m < 3; ++m) {
+        p.off_Q[m] = take(sizeof(float) * N * d);
+        p.off_dxh[m] = take(sizeof(float) * p.jsplit * n * d);
+        if (tc) {
+            p.off_xh[m] = take(2 * static_cast<size_t>(N) * p.dpad);
+            p.off_xhT[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad);
+        }
+    }
+    p.off_u = take(sizeof(float) * 3 * N);
+    p.off_v = take(sizeof(float) * 3 * N);
+    p.off_rowpart = take(sizeof(float) * p.row_parts * n);
+    p.off_colpart = take(sizeof(float) * p.col_parts * N);
+    p.off_posrow = take(sizeof(float) * n);
+    p.off_dots = take(sizeof(float) * 3 * n);
+    p.off_red = take(sizeof(double) * 512);
+    p.total = off;
+    return p;
+}
+
+static const int kPairA[3] = {0, 0, 1};
+static const int kPairB[3] = {1, 2, 2};
+
+static int check_common(const void* const x[3], const float* const inv_norm[3], const float pair_weight[3],
+                        int64_t N, int64_t d, int64_t row0, int64_t n, int dtype, int path, void* scratch,
+                        int64_t scratch_bytes, const LossPlan& plan) {
+    CLIBD_REQUIRE(N > 0 && d > 0 && n >= 0 && row0 >= 0 && row0 + n <= N, "bad row range");
+    CLIBD_REQUIRE(N < (int64_t(1) << 31) - 512, "n_global too large for 32-bit TMA coordinates");
+    CLIBD_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, "dtype must be 0, 1 or 2");
+    CLIBD_REQUIRE(path >= 0 && path <= 2, "path must be 0, 1 or 2");
+    CLIBD_REQUIRE(scratch != nullptr && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] != 0.f) {
+            CLIBD_REQUIRE(x[kPairA[p]] && x[kPairB[p]] && inv_norm[kPairA[p]] && inv_norm[kPairB[p]],
+                          "a weighted pair references an absent modality");
+        }
+    }
+    return 0;
+}
+
+}  // namespace clibd
+
+using namespace clibd;
+
+extern "C" {
+
+int clibd_abi_version(void) { return CLIBD_ABI_VERSION; }
+
+const char* clibd_last_error(void) { return last_error().c_str(); }
+
+int clibd_device_supported(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+int clibd_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* inv_norm, clibd_stream_t stream) {
+    CLIBD_REQUIRE(x && inv_norm && n >= 0 && d > 0, "null pointer or bad shape");
+    return launch_row_inv_norm(x, dtype, n, d, inv_norm, stream);
+}
+
+int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path) {
+    if (n_global <= 0 || n_local < 0 || d <= 0 || path < 0 || path > 2) return -1;
+    return static_cast<int64_t>(make_loss_plan(n_global, n_local, d, path).total);
+}
+
+int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
+                             const int64_t* labels, int64_t N, int64_t d, int64_t row0, int64_t n,
+                             float logit_scale, const float pair_weight[3], int path, void* scratch,
+                             int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
+                             clibd_stream_t stream) {
+    const LossPlan plan = make_loss_plan(N, n, d, path);
+    int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
+    if (rc) return rc;
+    CLIBD_REQUIRE(labels && rowsum && colsum && pos, "null output pointer");
+    const bool tc = path != PATH_SIMT_F32;
+    if (tc) {
+        CLIBD_REQUIRE(clibd_device_supported(), "tcgen05 path needs a compute-capability 10.x device");
+        // exp(S - s) must not underflow for the whole row: |S| <= s, so 2*s*log2(e) must stay < 126
+        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f,
+                      "tcgen05 path supports 0 < logit_scale <= 43 (fixed-shift softmax); use path 0");
+    } else {
+        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f, "logit_scale must be in (0, 43]");
+    }
+    const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
+    int32_t* rep = at<int32_t>(scratch, plan.off_rep);
+    float* cnt = at<float>(scratch, plan.off_cnt);
+    float* gscale = at<float>(scratch, plan.off_gscale);
+    if ((rc = launch_label_stats(labels, N, rep, cnt, stream))) return rc;
+    if ((rc = launch_gscale(cnt, N, path, gscale, stream))) return rc;
+    bool used[3] = {false, false, false};
+    for (int p = 0; p < 3; ++p)
+        if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
+    for (int m = 0; m < 3; ++m) {
+        if (!used[m]) continue;
+        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], rep, cnt, N, d, at<float>(scratch, plan.off_Q[m]), stream)))
+            return rc;
+        if (tc) {
+            if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16,
+                                           at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream)))
+                return rc;
+        }
+    }
+    float* rowpart = at<float>(scratch, plan.off_rowpart);
+    float* colpart = at<float>(scratch, plan.off_colpart);
+    float* posrow = at<float>(scratch, plan.off_posrow);
+    double* red = at<double>(scratch, plan.off_red);
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] == 0.f) {
+            CLIBD_CHECK_CUDA(cudaMemsetAsync(pos + p, 0, sizeof(double), stream));
+            continue;
+        }
+        const int a = kPairA[p], b = kPairB[p];
+        if (tc) {
+            rc = tc_forward_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xh[b]), N, plan.dpad, row0,
+                                 n, logit_scale, fmt_bf16, rowpart, colpart, stream);
+        } else {
+            rc = simt_forward_pair(x[a], x[b], dtype, inv_norm[a], inv_norm[b], N, d, row0, n, logit_scale, rowpart,
+                                   colpart, stream);
+        }
+        if (rc) return rc;
+        if ((rc = launch_reduce_parts(rowpart, plan.row_parts, n, n, rowsum + p * N + row0, stream))) return rc;
+        if ((rc = launch_reduce_parts(colpart, plan.col_parts, N, N, colsum + p * N, stream))) return rc;
+        if ((rc = launch_pos_rows(x[a], dtype, inv_norm[a], at<float>(scratch, plan.off_Q[b]), rep, d, row0, n, posrow,
+                                  stream)))
+            return rc;
+        if ((rc = launch_sum_to_double(posrow, n, 1.0, red, pos + p, stream))) return rc;
+    }
+    return 0;
+}
+
+int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
+                              int path, void* scratch, int64_t scratch_bytes, const float* rowsum,
+                              const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
+    CLIBD_REQUIRE(N > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
+    const LossPlan plan = make_loss_plan(N, n, d, path);
+    CLIBD_REQUIRE(scratch && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
+    CLIBD_REQUIRE(rowsum && colsum && pos && loss_out, "null pointer");
+    return launch_loss_finish(N, logit_scale, pair_weight, at<float>(scratch, plan.off_cnt), rowsum, colsum, pos,
+                              at<float>(scratch, plan.off_u), at<float>(scratch, plan.off_v),
+                              at<double>(scratch, plan.off_red), loss_out, stream);
+}
+
+int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                        int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                        void* scratch, int64_t scratch_bytes, float grad_feat_scale, void* const dx[3],
+                        double* dscale_partial, clibd_stream_t stream) {
+    const LossPlan plan = make_loss_plan(N, n, d, path);
+    int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
+    if (rc) return rc;
+    CLIBD_REQUIRE(dscale_partial != nullptr, "null dscale_partial");
+    const bool tc = path != PATH_SIMT_F32;
+    const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
+    const int32_t* rep = at<int32_t>(scratch, plan.off_rep);
+    const float* gscale = at<float>(scratch, plan.off_gscale);
+    const float* u = at<float>(scratch, plan.off_u);
+    const float* v = at<float>(scratch, plan.off_v);
+    float* dots = at<float>(scratch, plan.off_dots);
+    double* red = at<double>(scratch, plan.off_red);
+    int n_mod_used = 0;
+    for (int m = 0; m < 3; ++m) {
+        // ordered sweeps that write rows of modality m: for every weighted pair containing m
+        int npart = 0;
+        const float* Qp[2] = {nullptr, nullptr};
+        float wp[2] = {0.f, 0.f};
+        float* dxh = at<float>(scratch, plan.off_dxh[m]);
+        for (int p = 0; p < 3; ++p) {
+            if (pair_weight[p] == 0.f) continue;
+            int other;
+            const float *rowcoef, *colcoef;
+            if (kPairA[p] == m) {          // m indexes the rows of S_p
+                other = kPairB[p];
+                rowcoef = u + p * N;
+                colcoef = v + p * N;
+            } else if (kPairB[p] == m) {   // m indexes the columns of S_p: sweep S_p^T
+                other = kPairA[p];
+                rowcoef = v + p * N;
+                colcoef = u + p * N;
+            } else {
+                continue;
+            }
+            if (tc) {
+                rc = tc_backward_rows(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xh[other]),
+                                      at<void>(scratch, plan.off_xhT[other]), N, plan.npad, d, plan.dpad, row0, n,
+                                      logit_scale, rowcoef, colcoef, gscale, pair_weight[p], npart > 0, plan.jsplit,
+                                      fmt_bf16, dxh, stream);
+            } else {
+                rc = simt_backward_rows(x[m], x[other], dtype, inv_norm[m], inv_norm[other], N, d, row0, n, logit_scale,
+                                        rowcoef, colcoef, pair_weight[p], npart > 0, dxh, stream);
+            }
+            if (rc) return rc;
+            Qp[npart] = at<float>(scratch, plan.off_Q[other]);
+            wp[npart] = pair_weight[p];
+            ++npart;
+        }
+        if (npart == 0) continue;
+        NormBwdArgs a;
+        a.x = x[m];
+        a.dtype = dtype;
+        a.inv_norm = inv_norm[m];
+        a.rep = rep;
+        a.dxh = dxh;
+        a.jsplit = plan.jsplit;
+        a.Qp[0] = Qp[0];
+        a.Qp[1] = Qp[1];
+        a.wp[0] = wp[0];
+        a.wp[1] = wp[1];
+        a.N = N;
+        a.d = d;
+        a.row0 = row0;
+        a.n = n;
+        a.scale = logit_scale;
+        a.grad_scale = grad_feat_scale;
+        a.dx = dx ? dx[m] : nullptr;
+        a.dots = dots + n_mod_used * n;
+        if ((rc = launch_normalize_bwd(a, stream))) return rc;
+        ++n_mod_used;
+    }
+    // dL/ds = (1 / (2 s)) * sum over modalities and rows of xhat_i . dxhat_i  (unit upstream grad)
+    if ((rc = launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5 / static_cast<double>(logit_scale), red,
+                                   dscale_partial, stream))) return rc;
+    return 0;
+}
+
+}  // extern "C"

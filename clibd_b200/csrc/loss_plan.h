@@ -1,0 +1,98 @@
+// Scratch layout and internal launch interfaces of the contrastive-loss path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace clibd {
+
+// tcgen05 tile geometry (loss_tc.cu)
+constexpr int FWD_BM = 128;   // rows of S per CTA tile
+constexpr int FWD_BN = 256;   // columns of S per CTA tile
+constexpr int BWD_BM = 128;   // rows of S (= rows of dX) per CTA
+constexpr int BWD_BJ = 128;   // columns of S per step
+constexpr int BWD_DCH = 384;  // columns of dX accumulated in TMEM per CTA
+// CUDA-core fp32 tile geometry (loss_simt.cu)
+constexpr int SIMT_T = 64;    // forward tile (rows == cols)
+constexpr int SIMT_BR = 32;   // backward rows per block
+
+struct LossPlan {
+    int64_t N = 0, n = 0, d = 0, dpad = 0, npad = 0;
+    int path = 0;
+    int jsplit = 1;          // backward: column range split across CTAs (partials summed later)
+    int64_t row_parts = 0;   // forward: number of row-sum partials per row
+    int64_t col_parts = 0;   // forward: number of col-sum partials per column
+    size_t off_rep = 0, off_cnt = 0, off_gscale = 0;
+    size_t off_xh[3] = {0, 0, 0}, off_xhT[3] = {0, 0, 0}, off_Q[3] = {0, 0, 0}, off_dxh[3] = {0, 0, 0};
+    size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
+    size_t off_red = 0;  // small double buffer for block reductions
+    size_t total = 0;
+};
+
+LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path);
+
+template <typename T>
+inline T* at(void* base, size_t off) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off);
+}
+
+// ---- support kernels (loss_support.cu); all return 0 / error code ------------------
+int launch_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* inv_norm, cudaStream_t s);
+// rep[i] = lowest index with the same label, cnt[i] = number of rows sharing label i
+int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cnt, cudaStream_t s);
+// gscale[0] = power-of-two scale applied to 16-bit G operands (1 for bf16), gscale[1] = 1/gscale[0]
+int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStream_t s);
+// Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r
+int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* rep, const float* cnt,
+                      int64_t N, int64_t d, float* Q, cudaStream_t s);
+// 16-bit normalised operand copies: xh [N,dpad] and its transpose xhT [dpad,npad] (zero padded)
+int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
+                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s);
+// posrow[i] = xhat_a[row0+i] . Qb[rep[row0+i]]
+int launch_pos_rows(const void* xa, int dtype, const float* inv_a, const float* Qb, const int32_t* rep, int64_t d,
+                    int64_t row0, int64_t n, float* posrow, cudaStream_t s);
+// out[k] = sum_{p < parts} part[p*stride + k] for k < len (fixed order)
+int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s);
+// out[0] = mul * sum_k in[k] in double, fixed order
+int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s);
+// loss + backward coefficients u = cnt/rowsum, v = cnt/colsum
+int launch_loss_finish(int64_t N, float scale, const float w[3], const float* cnt, const float* rowsum,
+                       const float* colsum, const double* pos, float* u, float* v, double* red, float* loss_out,
+                       cudaStream_t s);
+// dx = grad_scale * normalize_bwd( (scale/N) * (sum_splits dxh - 2 * sum_partners w_p Q_partner[rep]) );
+// dots[i] = xhat_i . dxhat_i for unit grad
+struct NormBwdArgs {
+    const void* x;
+    int dtype;
+    const float* inv_norm;
+    const int32_t* rep;
+    const float* dxh;       // [jsplit][n][d]
+    int jsplit;
+    const float* Qp[2];     // partner class sums (may be null)
+    float wp[2];            // their pair weights
+    int64_t N, d, row0, n;
+    float scale, grad_scale;
+    void* dx;               // [n,d] in dtype, may be null
+    float* dots;            // [n]
+};
+int launch_normalize_bwd(const NormBwdArgs& a, cudaStream_t s);
+
+// ---- CUDA-core fp32 path (loss_simt.cu) ---------------------------------------------
+int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* inv_a, const float* inv_b, int64_t N,
+                      int64_t d, int64_t row0, int64_t n, float scale, float* rowpart, float* colpart,
+                      cudaStream_t s);
+// dxh[n,d] (+)= weight * sum_j e_ij (rowcoef_i + colcoef_j) yhat_j   for local rows i of x
+int simt_backward_rows(const void* x, const void* y, int dtype, const float* inv_x, const float* inv_y, int64_t N,
+                       int64_t d, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
+                       float weight, int accumulate, float* dxh, cudaStream_t s);
+
+// ---- tcgen05 path (loss_tc.cu) --------------------------------------------------------
+int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
+                    int fmt_bf16, float* rowpart, float* colpart, cudaStream_t s);
+int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
+                     int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
+                     const float* gscale, float weight, int accumulate, int jsplit, int fmt_bf16, float* dxh,
+                     cudaStream_t s);
+
+}  // namespace clibd

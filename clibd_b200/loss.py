@@ -1,0 +1,304 @@
+"""Drop-in replacements for bioscanclip/model/loss_func.py, backed by the sm_100a CUDA library.
+
+Same names, constructor arguments, forward signatures and error behaviour as the reference:
+
+  * ``construct_label_metrix``   loss_func.py:19-22
+  * ``ContrastiveLoss``          loss_func.py:25-69
+  * ``gather_features``          loss_func.py:73-106
+  * ``ClipLoss``                 loss_func.py:110-201
+
+The N x N logit / target matrices of the reference are never materialised: the fused
+kernels (csrc/loss_tc.cu, csrc/loss_simt.cu) produce row/column log-sum-exp statistics in
+their epilogue and the label-matched positive term is an O(N d) class sum.  Multi-GPU:
+each rank owns its row block; features, inverse norms and labels are all-gathered
+(torch.distributed / NCCL), per-rank statistics are all-reduced, and every rank produces
+the gradient of ITS rows directly, scaled by sum_r grad_out_r -- the reduce-scatter(SUM)
+convention of torch.distributed.nn.all_gather's backward (loss_func.py:97).
+
+There is no CPU or eager-PyTorch fallback: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+try:  # same optional import dance as loss_func.py:5-11
+    import torch.distributed.nn  # noqa: F401
+    from torch import distributed as dist
+
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+_MODALITY_INDEX = {"image": 0, "dna": 1, "text": 2}  # loss_func.py:166-173
+_PAIR_SLOT = {(0, 1): 0, (0, 2): 1, (1, 2): 2}
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
+
+
+def construct_label_metrix(labels):
+    """loss_func.py:19-22 (kept for API parity; the fused loss never builds this matrix)."""
+    return (labels.unsqueeze(0) == labels.unsqueeze(1)).float()
+
+
+def pair_weights(present, bind_to=None, no_image_text_loss=False):
+    """Weights of the unordered slot pairs (image,dna), (image,text), (dna,text) that make
+    sum_p w_p [CE(S_p,T) + CE(S_p^T,T)] equal the reference's mean over its loss list.
+
+    The reference loops over ordered pairs of the None-FILTERED feature list and applies the
+    bind_to / no_image_text indices to that filtered list (loss_func.py:159-184); each visit
+    appends both directions (loss_func.py:195-198)."""
+    slots = [i for i, p in enumerate(present) if p]
+    bind_to_idx = _MODALITY_INDEX.get(bind_to) if bind_to is not None else None
+    visits = {}
+    n_ordered = 0
+    for a in range(len(slots)):
+        for b in range(len(slots)):
+            if bind_to_idx is not None and a != bind_to_idx and b != bind_to_idx:
+                continue
+            if a == b:
+                continue
+            if no_image_text_loss and (a == 0 or b == 0) and (a == 2 or b == 2):
+                continue
+            n_ordered += 1
+            key = (min(slots[a], slots[b]), max(slots[a], slots[b]))
+            visits[key] = visits.get(key, 0) + 1
+    w = [0.0, 0.0, 0.0]
+    for key, m in visits.items():
+        w[_PAIR_SLOT[key]] = m / (2.0 * n_ordered)
+    return w, n_ordered
+
+
+def _select_path(dtype, operands):
+    if operands is None:
+        return {torch.float32: _lib.PATH_SIMT_F32, torch.bfloat16: _lib.PATH_TC_BF16,
+                torch.float16: _lib.PATH_TC_F16}[dtype]
+    return {"fp32": _lib.PATH_SIMT_F32, "bf16": _lib.PATH_TC_BF16, "fp16": _lib.PATH_TC_F16}[operands]
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _FusedClipLossFn(torch.autograd.Function):
+    """forward(image, dna, text, labels, scale_tensor|None, scale_value, weights, path, group, world, rank,
+    sum_grad_over_ranks) -> 0-d float32 loss"""
+
+    @staticmethod
+    def forward(ctx, image, dna, text, labels, scale_tensor, scale_value, weights, path, group, world, rank,
+                sum_grads):
+        lib = _lib.load()
+        feats = [image, dna, text]
+        ref = next(f for f in feats if f is not None)
+        device, dtype = ref.device, ref.dtype
+        n, d = ref.shape
+        stream = _stream_ptr(device)
+        with torch.cuda.device(device):
+            local = [None if f is None else f.detach().contiguous() for f in feats]
+            inv_local = []
+            for f in local:
+                if f is None:
+                    inv_local.append(None)
+                    continue
+                iv = torch.empty(n, dtype=torch.float32, device=device)
+                _lib.check(lib.clibd_row_inv_norm(f.data_ptr(), _DT[dtype], n, d, iv.data_ptr(), stream))
+                inv_local.append(iv)
+            labels = labels.detach().to(device=device, dtype=torch.int64).contiguous()
+            if world > 1:
+                N = n * world
+                gathered, inv = [], []
+                for f, iv in zip(local, inv_local):
+                    if f is None:
+                        gathered.append(None)
+                        inv.append(None)
+                        continue
+                    g = torch.empty((N, d), dtype=dtype, device=device)
+                    dist.all_gather_into_tensor(g, f, group=group)
+                    gi = torch.empty(N, dtype=torch.float32, device=device)
+                    dist.all_gather_into_tensor(gi, iv, group=group)
+                    gathered.append(g)
+                    inv.append(gi)
+                all_labels = torch.empty(N, dtype=torch.int64, device=device)
+                dist.all_gather_into_tensor(all_labels, labels, group=group)
+                row0 = rank * n
+            else:
+                N, gathered, inv, all_labels, row0 = n, local, inv_local, labels, 0
+            nbytes = lib.clibd_loss_scratch_bytes(N, n, d, path)
+            if nbytes < 0:
+                raise ValueError("clibd_b200: bad loss shape")
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            stats = torch.zeros(6 * N, dtype=torch.float32, device=device)  # rowsum[3][N] | colsum[3][N]
+            pos = torch.zeros(3, dtype=torch.float64, device=device)
+            xs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in gathered])
+            ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in inv])
+            w = _lib.float_array3(weights)
+            rowsum_ptr = stats.data_ptr()
+            colsum_ptr = stats.data_ptr() + 4 * 3 * N
+            _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, all_labels.data_ptr(), N, d, row0, n,
+                                                    scale_value, w, path, scratch.data_ptr(), nbytes, rowsum_ptr,
+                                                    colsum_ptr, pos.data_ptr(), stream))
+            if world > 1:
+                dist.all_reduce(stats, group=group)  # row sums have disjoint support, column sums add up
+                dist.all_reduce(pos, group=group)
+            loss = torch.empty((), dtype=torch.float32, device=device)
+            _lib.check(lib.clibd_loss_forward_finish(N, n, d, scale_value, w, path, scratch.data_ptr(), nbytes,
+                                                     rowsum_ptr, colsum_ptr, pos.data_ptr(), loss.data_ptr(),
+                                                     stream))
+        ctx.gathered, ctx.inv, ctx.scratch = gathered, inv, scratch
+        ctx.meta = (N, n, d, row0, scale_value, tuple(weights), path, group, world, dtype, device, sum_grads)
+        ctx.has_scale = scale_tensor is not None
+        ctx.scale_dtype = scale_tensor.dtype if scale_tensor is not None else None
+        ctx.present = [f is not None for f in feats]
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        N, n, d, row0, scale_value, weights, path, group, world, dtype, device, sum_grads = ctx.meta
+        stream = _stream_ptr(device)
+        with torch.cuda.device(device):
+            grad_out = grad_out.detach().to(device=device, dtype=torch.float32).reshape(())
+            dxs = [torch.empty((n, d), dtype=dtype, device=device) if (p and ctx.needs_input_grad[i]) else None
+                   for i, p in enumerate(ctx.present)]
+            dscale = torch.zeros(1, dtype=torch.float64, device=device)
+            xs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in ctx.gathered])
+            ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in ctx.inv])
+            outs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in dxs])
+            w = _lib.float_array3(weights)
+            _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path,
+                                               ctx.scratch.data_ptr(), ctx.scratch.numel(), 1.0, outs,
+                                               dscale.data_ptr(), stream))
+            gsum = grad_out
+            if world > 1:
+                if sum_grads:  # backward of the differentiable all-gather: reduce-scatter(SUM) over ranks
+                    gsum = grad_out.clone()
+                    dist.all_reduce(gsum, group=group)
+                dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
+            grads = [None if g is None else (g.float() * gsum).to(dtype) if dtype != torch.float32 else g * gsum
+                     for g in dxs]
+            gscale = None
+            if ctx.has_scale and ctx.needs_input_grad[4]:
+                gscale = (dscale[0] * grad_out.double()).to(ctx.scale_dtype).reshape(())
+        return grads[0], grads[1], grads[2], None, gscale, None, None, None, None, None, None, None
+
+
+def _validate_criterion(criterion):
+    if criterion is None:
+        return
+    ok = isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean" \
+        and getattr(criterion, "label_smoothing", 0.0) == 0.0 and criterion.weight is None
+    if not ok:
+        raise NotImplementedError(
+            "clibd_b200 fuses nn.CrossEntropyLoss() with default arguments (the only criterion the reference "
+            "constructs, train_cl.py:260,262); other criteria are not supported")
+
+
+def _fused_loss(image_features, dna_features, text_features, labels, logit_scale, bind_to, no_image_text_loss,
+                operands, group, world, rank, sum_grads):
+    feats = [image_features, dna_features, text_features]
+    present = [f is not None for f in feats]
+    if sum(present) < 2:
+        raise ValueError("Too less element for calculating the contrastive loss.")  # loss_func.py:46-47,162-163
+    ref = next(f for f in feats if f is not None)
+    if not ref.is_cuda:
+        raise RuntimeError("clibd_b200 runs on CUDA tensors only (there is no CPU fallback)")
+    shapes = {tuple(f.shape) for f in feats if f is not None}
+    if len(shapes) != 1 or ref.dim() != 2:
+        raise ValueError("all feature tensors must share one [batch, dim] shape")
+    if ref.shape[0] == 0:
+        raise ValueError("empty batch")
+    dtypes = {f.dtype for f in feats if f is not None}
+    if len(dtypes) != 1 or ref.dtype not in _DT:
+        common = torch.float32
+        feats = [None if f is None else f.to(common) for f in feats]
+    else:
+        common = ref.dtype
+    weights, n_ordered = pair_weights(present, bind_to, no_image_text_loss)
+    if n_ordered == 0:
+        raise ZeroDivisionError("float division by zero")  # reference: sum([]) * 1.0 / len([])
+    scale_tensor = logit_scale if isinstance(logit_scale, torch.Tensor) else None
+    scale_value = float(logit_scale)  # one host read when the scale is a tensor (the reference reads loss.item())
+    path = _select_path(common, operands)
+    return _FusedClipLossFn.apply(feats[0], feats[1], feats[2], labels, scale_tensor, scale_value, weights, path,
+                                  group, world, rank, sum_grads)
+
+
+class ContrastiveLoss(nn.Module):
+    """Single-process contrastive loss, reference loss_func.py:25-69."""
+
+    def __init__(self, criterion, logit_scale, local_loss=False, gather_with_grad=False, rank=0, world_size=1,
+                 use_horovod=False, tensor_core_operands=None):
+        super().__init__()
+        _validate_criterion(criterion)
+        self.criterion = criterion
+        self.logit_scale = logit_scale
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.prev_num_logits = 0
+        self.labels = {}
+        # None: fp32 inputs -> exact CUDA-core path, bf16/fp16 inputs -> tcgen05 with that operand type;
+        # "bf16" / "fp16" force the tensor-core path, "fp32" forces the CUDA-core path.
+        self.tensor_core_operands = tensor_core_operands
+
+    def forward(self, image_features, dna_features, text_features, labels, logit_scale):
+        scale = logit_scale if logit_scale is not None else self.logit_scale  # loss_func.py:58-63
+        return _fused_loss(image_features, dna_features, text_features, labels, scale, None, False,
+                           self.tensor_core_operands, None, 1, 0, True)
+
+
+def gather_features(features, local_loss=False, gather_with_grad=False, rank=0, world_size=1, use_horovod=False):
+    """loss_func.py:73-106 (public helper of the reference module; the fused ClipLoss does not call it)."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if use_horovod:
+        raise NotImplementedError("horovod is not supported (no shipped reference config uses it)")
+    if gather_with_grad:
+        return torch.cat(torch.distributed.nn.all_gather(features), dim=0)
+    gathered = [torch.zeros_like(features) for _ in range(world_size)]
+    dist.all_gather(gathered, features)
+    if not local_loss:
+        gathered[rank] = features
+    return torch.cat(gathered, dim=0)
+
+
+class ClipLoss(nn.Module):
+    """All-gather contrastive loss, reference loss_func.py:110-201."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False, criterion=None, bind_to=None, no_image_text_loss=False,
+                 tensor_core_operands=None, process_group=None):
+        super().__init__()
+        _validate_criterion(criterion)
+        if use_horovod:
+            raise NotImplementedError("horovod is not supported (no shipped reference config uses it)")
+        if world_size > 1 and local_loss and not gather_with_grad:
+            raise NotImplementedError("local_loss=True without gather_with_grad detaches every gathered feature "
+                                      "in the reference (loss_func.py:99-104); not supported")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.criterion = criterion if criterion is not None else nn.CrossEntropyLoss()
+        self.prev_num_logits = 0
+        self.labels = {}
+        self.bind_to = bind_to
+        self.no_image_text_loss = no_image_text_loss
+        self.tensor_core_operands = tensor_core_operands
+        self.process_group = process_group
+
+    def forward(self, image_features, dna_features, text_features, labels, logit_scale, output_dict=False):
+        if self.world_size > 1 and not (has_distributed and dist.is_initialized()):
+            raise RuntimeError("ClipLoss(world_size>1) needs an initialised torch.distributed process group")
+        # gather_with_grad=True: local grads are summed over every rank's loss (reduce-scatter);
+        # gather_with_grad=False, local_loss=False: only this rank's loss reaches the local slot.
+        total_loss = _fused_loss(image_features, dna_features, text_features, labels, logit_scale, self.bind_to,
+                                 self.no_image_text_loss, self.tensor_core_operands, self.process_group,
+                                 self.world_size, self.rank, bool(self.gather_with_grad))
+        return {"contrastive_loss": total_loss} if output_dict else total_loss

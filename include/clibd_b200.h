@@ -1,0 +1,122 @@
+/* clibd_b200 -- C ABI of the B200-native CLIBD hot path (sm_100a).
+ *
+ * The reference (bioscan-ml/clibd) is pure Python and has no FFI; these entry points
+ * are what a binding for its hot path would call.  Each one names the reference
+ * interface it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer unless its comment says "host";
+ *   - the caller owns all memory (inputs, outputs, scratch); the library never
+ *     allocates, frees or retains device memory past the call;
+ *   - all work is enqueued asynchronously on `stream`;
+ *   - return 0 = ok, non-zero = error; text via clibd_last_error() (thread-local);
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16;
+ *   - path codes : 0 = CUDA-core fp32 (exact, any N/d),
+ *                  1 = tcgen05 tensor cores, bf16 operands, fp32 accumulate,
+ *                  2 = tcgen05 tensor cores, f16 operands, fp32 accumulate.
+ *   - feature slots are always [image, dna, text]; an absent modality is NULL;
+ *   - pair_weight[3] weights the unordered pairs (image,dna), (image,text), (dna,text):
+ *     the loss is sum_p pair_weight[p] * [CE(S_p, T) + CE(S_p^T, T)], so the reference's
+ *     "mean over the filtered ordered-pair list" (loss_func.py:69,200) is
+ *     pair_weight[p] = multiplicity_p / len(loss_list).
+ */
+#ifndef CLIBD_B200_H
+#define CLIBD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
+
+#define CLIBD_ABI_VERSION 1
+
+int clibd_abi_version(void);
+const char* clibd_last_error(void);
+/* 1 if the current device is compute capability 10.x (the tcgen05 paths need it). */
+int clibd_device_supported(void);
+
+/* ---- contrastive loss ------------------------------------------------------------
+ * Replaces ContrastiveLoss.forward / ClipLoss.forward and their autograd backward
+ * (bioscanclip/model/loss_func.py:41-69, :138-201) and construct_label_metrix (:19-22).
+ * Phases are split where the reference all-gathers (loss_func.py:143-157) so the host
+ * can run the collectives between them; with one process call them back to back. */
+
+/* inv_norm[i] = 1 / max(||x_i||_2, 1e-12)  (F.normalize, loss_func.py:55-56,186-187) */
+int clibd_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* inv_norm, clibd_stream_t stream);
+
+/* Bytes of scratch the three loss calls below need (same scratch, kept from forward
+ * to backward). */
+int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path);
+
+/* Forward statistics for the local row block [row0, row0+n_local) against all n_global
+ * columns.  x[m]: gathered [n_global, d] row-major features in `dtype`; inv_norm[m]:
+ * [n_global]; labels: [n_global] int64.
+ * Writes rowsum[p*n_global + i] for LOCAL rows i (sum_j exp(S_ij - s)), colsum[p*n_global + j]
+ * for all j summed over the local rows only (all-reduce it across ranks), and
+ * pos[p] = sum_{i local} sum_j T_ij * cos_ij (all-reduce it). */
+int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
+                             const int64_t* labels, int64_t n_global, int64_t d, int64_t row0, int64_t n_local,
+                             float logit_scale, const float pair_weight[3] /* host */, int path, void* scratch,
+                             int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
+                             clibd_stream_t stream);
+
+/* Loss value from complete statistics (rowsum/colsum/pos now hold GLOBAL sums for all
+ * n_global rows/columns); also prepares the backward coefficients inside scratch. */
+int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, float logit_scale,
+                              const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
+                              const float* rowsum, const float* colsum, const double* pos, float* loss_out,
+                              clibd_stream_t stream);
+
+/* Backward for the local rows.  dx[m]: [n_local, d] in `dtype` (NULL to skip) receives
+ * grad_feat_scale * dL/dx; dscale_partial[0] receives sum over the local rows'
+ * contribution to dL/d(logit_scale) for unit upstream gradient (all-reduce, then
+ * multiply by the rank's own grad_output).  grad_feat_scale = sum over ranks of
+ * grad_output (the reduce-scatter(SUM) convention of torch.distributed.nn.all_gather,
+ * loss_func.py:97). */
+int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
+                        int64_t d, int64_t row0, int64_t n_local, float logit_scale,
+                        const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
+                        float grad_feat_scale, void* const dx[3], double* dscale_partial, clibd_stream_t stream);
+
+/* ---- cosine nearest-neighbour retrieval --------------------------------------------
+ * Replaces make_prediction / find_closest_match's search (bioscanclip/util/util.py:
+ * 521-528, 759-766): sklearn L2-normalise (float64) -> float32, faiss IndexFlatIP
+ * add + search(k), with ties broken by LOWEST index. */
+
+/* out[i,:] = float32( x[i,:] / ||x[i,:]||_2 ) with the norm and division in float64;
+ * zero rows stay zero.  x dtype: 0 = float32, 3 = float64. */
+int clibd_knn_normalize(const void* x, int dtype, int64_t n, int64_t d, float* out, clibd_stream_t stream);
+
+int64_t clibd_knn_scratch_bytes(int64_t n_query, int64_t n_key, int64_t d, int k, int path);
+
+/* Exact top-k of q32 [n_query,d] against keys32 [n_key,d] (both already normalised
+ * float32).  Similarity = float64 sum over d, in index order, of the exact products;
+ * order key (-sim, index).  Global index = key_offset + local row.  path 1/2 screen with
+ * tcgen05 16-bit operands and re-rank candidates exactly (queries whose screen cannot be
+ * proven complete are re-done exhaustively in float64); path 0 is exhaustive float64.
+ * n_exhaustive (device, int32[1]) receives how many queries took the exhaustive route. */
+int clibd_knn_search(const float* q32, int64_t n_query, const float* keys32, int64_t n_key, int64_t key_offset,
+                     int64_t d, int k, int path, void* scratch, int64_t scratch_bytes, double* out_sims64,
+                     int64_t* out_idx, int32_t* n_exhaustive, clibd_stream_t stream);
+
+/* Merge `parts` per-shard results [parts, n_query, k] into the global top-k by (-sim, index). */
+int clibd_knn_merge(const double* sims64, const int64_t* idx, int parts, int64_t n_query, int k,
+                    double* out_sims64, float* out_sims32, int64_t* out_idx, clibd_stream_t stream);
+
+/* ---- top-k accuracy ------------------------------------------------------------------
+ * Replaces top_k_micro_accuracy (util.py:379-395) and top_k_macro_accuracy (:555-599)
+ * on integer label ids.  idx: [n_query, kmax] global key indices; key_ids: [n_key, 4]
+ * ids per level (order, family, genus, species); query_ids: [n_query, 4];
+ * k_list: host array of nk values <= kmax; n_class[l]: ids at level l are in [0, n_class[l]).
+ * hits:  [nk, 4, n_query] uint8 scratch; class_hit/class_cnt: [nk, 4, max_class] int32 scratch
+ * (zeroed by the call).  Outputs are COUNTS so the host reproduces the reference's float
+ * arithmetic exactly: micro_hits [nk,4] int64; class_hit/class_cnt hold per-class counts. */
+int clibd_topk_accuracy(const int64_t* idx, int64_t n_query, int kmax, const int32_t* key_ids, int64_t n_key,
+                        const int32_t* query_ids, const int32_t* k_list /* host */, int nk, int32_t max_class,
+                        int64_t* micro_hits, int32_t* class_hit, int32_t* class_cnt, clibd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIBD_B200_H */

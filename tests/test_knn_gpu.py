@@ -1,0 +1,183 @@
+"""GPU parity tests of the cosine kNN retrieval + accuracy path (through the C ABI) against the
+CPU oracle: indices bit-exact under the lowest-index tie-break, accuracies bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def _taxonomy_data(Q, K, D, seed, n_species=200, noise=0.02, dup=0):
+    """class-centroid + noise embeddings with a 4-level taxonomy and exact duplicate keys."""
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((n_species, D)) / np.sqrt(D)
+    sp_k = rng.integers(0, n_species, K)
+    sp_q = rng.integers(0, n_species, Q)
+    keys = cent[sp_k] + noise * rng.standard_normal((K, D))
+    q = cent[sp_q] + noise * rng.standard_normal((Q, D))
+    if dup:
+        src = rng.integers(0, K, dup)
+        dst = rng.integers(0, K, dup)
+        keys[dst] = keys[src]
+        sp_k[dst] = sp_k[src]
+    def ids(sp):
+        return np.stack([sp % 4, sp % 17, sp % 61, sp], axis=1).astype(np.int32)
+    return q, keys, ids(sp_q), ids(sp_k)
+
+
+def _ulp_close(a, b):
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    return np.all(np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64)) <= 1)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fp16", "bf16"])
+@pytest.mark.parametrize("Q,K,D,k", [(300, 5000, 96, 5), (257, 1031, 45, 3), (64, 700, 768, 10)])
+def test_search_matches_oracle_small(mode, Q, K, D, k):
+    import clibd_b200 as cb
+    q, keys, _, _ = _taxonomy_data(Q, K, D, seed=3, dup=K // 20)
+    q[7] = keys[11]
+    s32, idx = cb.knn_search(q, keys, k, mode=mode, device="cuda:0")
+    ref_s, ref_i, _ = ko.search(ko.normalize_rows(q), ko.normalize_rows(keys), k)
+    assert np.array_equal(idx.cpu().numpy(), ref_i)
+    assert _ulp_close(s32.cpu().numpy(), ref_s)
+
+
+def test_search_matches_oracle_medium_with_duplicates():
+    """d=768, 50k keys, 2k queries, >= 1000 exact duplicate keys (scaled so
+    the C oracle finishes in seconds)."""
+    import clibd_b200 as cb
+    Q, K, D, k = 2048, 50000, 768, 5
+    q, keys, qid, kid = _taxonomy_data(Q, K, D, seed=4, n_species=2000, dup=1500)
+    q = q.astype(np.float32)
+    keys = keys.astype(np.float32)
+    ref_s, ref_i, _ = ko.search(ko.normalize_rows(q), ko.normalize_rows(keys), k)
+    for mode in ("fp16", "bf16", "exact"):
+        s32, idx = cb.knn_search(q, keys, k, mode=mode, device="cuda:0")
+        assert np.array_equal(idx.cpu().numpy(), ref_i), mode
+        assert _ulp_close(s32.cpu().numpy(), ref_s)
+    # accuracy counts vs the oracle's integer-id form, bit for bit
+    from clibd_b200 import retrieval as R
+    dev = torch.device("cuda:0")
+    k_list = [1, 3, 5]
+    micro, chit, ccnt = R.accuracy_counts(torch.from_numpy(ref_i).to(dev), torch.from_numpy(kid).to(dev),
+                                          torch.from_numpy(qid).to(dev), k_list, 2000)
+    mi = micro.cpu().numpy() * 1.0 / Q
+    assert np.array_equal(mi, ko.micro_accuracy_ids(ref_i, kid, qid, k_list))
+    ma_ref = ko.macro_accuracy_ids(ref_i, kid, qid, k_list)
+    chit, ccnt = chit.cpu().numpy(), ccnt.cpu().numpy()
+    for a in range(3):
+        for l in range(4):
+            _, first = np.unique(qid[:, l], return_index=True)
+            total = 0.0
+            order = qid[np.sort(first), l]
+            for c in order:
+                total = total + chit[a, l, c] * 1.0 / ccnt[a, l, c]
+            assert total / len(order) == ma_ref[a, l]
+
+
+def test_many_identical_keys_lowest_index_wins():
+    """Every sample of a taxon has the same text embedding (dataset.py:150-153): far more exact
+    duplicates than a candidate list holds -- the exhaustive fallback must kick in and still be exact."""
+    import clibd_b200 as cb
+    rng = np.random.default_rng(9)
+    base = rng.standard_normal((40, 64))
+    keys = base[rng.integers(0, 40, 6000)]
+    q = base[rng.integers(0, 40, 100)] + 0.01 * rng.standard_normal((100, 64))
+    ref_s, ref_i, _ = ko.search(ko.normalize_rows(q), ko.normalize_rows(keys), 5)
+    for mode in ("fp16", "exact"):
+        s32, idx = cb.knn_search(q, keys, 5, mode=mode, device="cuda:0")
+        assert np.array_equal(idx.cpu().numpy(), ref_i), mode
+
+
+def test_shard_merge_equals_unsharded():
+    from clibd_b200 import retrieval as R
+    dev = torch.device("cuda:0")
+    q, keys, _, _ = _taxonomy_data(500, 9001, 128, seed=6, dup=400)
+    q32, k32 = R.normalize_rows(q, dev), R.normalize_rows(keys, dev)
+    s_all, i_all, _ = R.search_normalized(q32, k32, 5, mode="fp16")
+    bounds = [0, 3000, 3001, 9001]
+    parts_s, parts_i = [], []
+    for lo_, hi_ in zip(bounds[:-1], bounds[1:]):
+        kk = min(5, hi_ - lo_)
+        s, i, _ = R.search_normalized(q32, k32[lo_:hi_].contiguous(), kk, key_offset=lo_, mode="fp16")
+        if kk < 5:
+            s = torch.cat([s, torch.full((500, 5 - kk), -1.7e308, dtype=torch.float64, device=dev)], 1)
+            i = torch.cat([i, torch.full((500, 5 - kk), -1, dtype=torch.int64, device=dev)], 1)
+        parts_s.append(s)
+        parts_i.append(i)
+    m64, m32, mi = R.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, i_all) and torch.equal(m64, s_all)
+    assert torch.equal(m32, s_all.float())
+
+
+def test_make_prediction_and_eval_entry_point_match_oracle():
+    import clibd_b200 as cb
+    rng = np.random.default_rng(12)
+    D, K = 48, 900
+    q_seen, keys, qid_s, kid = _taxonomy_data(150, K, D, seed=13, n_species=60, dup=50)
+    q_unseen, _, qid_u, _ = _taxonomy_data(120, K, D, seed=14, n_species=60)
+    def lab(ids):
+        return [{l: f"{l}_{int(r[i])}" for i, l in enumerate(ko.LEVELS)} for r in ids]
+    key_labels, seen_labels, unseen_labels = lab(kid), lab(qid_s), lab(qid_u)
+    # make_prediction: return convention + content
+    p, s, i = cb.make_prediction(q_seen, keys, key_labels, with_similarity=True, with_indices=True, max_k=5)
+    rp, rs, ri = ko.make_prediction(q_seen, keys, key_labels, with_similarity=True, with_indices=True, max_k=5)
+    assert p == rp and np.array_equal(i, ri) and _ulp_close(s, rs)
+    assert cb.make_prediction(q_seen, keys, key_labels, max_k=5) == rp
+    fc = cb.find_closest_match(q_seen, keys, key_labels, with_indices=True, max_k=3)
+    assert set(fc) == {"pred_list", "indices"} and np.array_equal(fc["indices"], ri[:, :3])
+    # reference-signature accuracy functions
+    k_list = [1, 3, 5]
+    assert cb.top_k_micro_accuracy(rp, seen_labels, k_list=k_list) == ko.micro_accuracy_ref_style(rp, seen_labels, k_list)
+    ma, pc = cb.top_k_macro_accuracy(rp, seen_labels, k_list=k_list)
+    rma, rpc = ko.macro_accuracy_ref_style(rp, seen_labels, k_list)
+    assert ma == rma and pc == rpc
+    # eval entry point on two feature types (+ a width mismatch that must be skipped)
+    img_k, dna_k = keys, keys[::-1].copy()
+    keys_dict = {"label_list": key_labels, "encoded_image_feature": img_k, "encoded_dna_feature": dna_k,
+                 "concatenated_feature": np.concatenate([img_k, dna_k], 1), "encoded_language_feature": None,
+                 "all_key_features": np.concatenate([img_k, dna_k], 0), "all_key_features_label": key_labels * 2}
+    seen = {"label_list": seen_labels, "file_name_list": list(range(150)), "encoded_image_feature": q_seen,
+            "encoded_dna_feature": q_seen * 0.5}
+    unseen = {"label_list": unseen_labels, "file_name_list": list(range(120)), "encoded_image_feature": q_unseen,
+              "encoded_dna_feature": q_unseen * 2.0}
+    acc, per_class, pred = cb.inference_and_print_result(keys_dict, seen, unseen, args=None, k_list=k_list, verbose=False)
+    assert acc["encoded_image_feature"]["concatenated_feature"] == {}
+    for qt in ("encoded_image_feature", "encoded_dna_feature"):
+        for kt, kf, kl in (("encoded_image_feature", img_k, key_labels), ("encoded_dna_feature", dna_k, key_labels),
+                           ("all_key_features", keys_dict["all_key_features"], key_labels * 2)):
+            for split, qf, gl in (("seen", seen[qt], seen_labels), ("unseen", unseen[qt], unseen_labels)):
+                rp_ = ko.make_prediction(qf, kf, kl, max_k=5)
+                assert pred[qt][kt][f"curr_{split}_pred_list"] == rp_
+                assert acc[qt][kt][split]["micro_acc"] == ko.micro_accuracy_ref_style(rp_, gl, k_list)
+                rma_, rpc_ = ko.macro_accuracy_ref_style(rp_, gl, k_list)
+                assert acc[qt][kt][split]["macro_acc"] == rma_
+                assert per_class[qt][kt][split] == rpc_
+    assert pred["seen_id"] == list(range(150))
+
+
+def test_large_search_properties():
+    """200k keys x 20k queries (d=768): no oracle; the queries are copies of keys, so the best match
+    must be the lowest-index copy of that key with similarity 1, results sorted and duplicate-free."""
+    from clibd_b200 import retrieval as R
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    K, Q, D = 200_000, 20_000, 768
+    keys = torch.randn(K, D, device=dev, generator=gen)
+    keys[150_000:150_500] = keys[10_000:10_500]  # duplicates: the lower index must win
+    pick = torch.randint(0, K, (Q,), device=dev, generator=gen)
+    pick[:500] = torch.arange(150_000, 150_500, device=dev)
+    q32, k32 = R.normalize_rows(keys[pick], dev), R.normalize_rows(keys, dev)
+    s64, idx, nex = R.search_normalized(q32, k32, 5, mode="fp16")
+    expect = pick.clone()
+    expect[:500] = torch.arange(10_000, 10_500, device=dev)
+    dup_src = (pick >= 10_000) & (pick < 10_500)
+    assert torch.equal(idx[:, 0][~dup_src], expect[~dup_src])
+    assert torch.all(s64[:, 0] > 0.999999)
+    assert torch.all(s64[:, :-1] >= s64[:, 1:])
+    srt = torch.sort(idx, dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1])
+    assert int(nex) < Q // 10
