@@ -21,6 +21,9 @@ SIGNATURES = {
     "clibd_abi_version": (_INT, []),
     "clibd_last_error": (_c.c_char_p, []),
     "clibd_device_supported": (_INT, []),
+    "clibd_kernel_launch_count": (_I64, []),
+    "clibd_profile_enable": (_INT, [_INT]),
+    "clibd_profile_read": (_INT, [_P, _P]),
     "clibd_row_inv_norm": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
     "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P,

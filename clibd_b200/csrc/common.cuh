@@ -16,6 +16,17 @@ enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 enum : int { PATH_SIMT_F32 = 0, PATH_TC_BF16 = 1, PATH_TC_F16 = 2 };
 
 void set_error(const std::string& msg);
+// telemetry (loss_api.cu): number of kernels this library launched, and optional CUDA-event timing
+// of the tensor-core kernels on their launching stream (slots below)
+void count_launch();
+enum : int { PROF_LOSS_FWD_TC = 0, PROF_LOSS_BWD_TC = 1, PROF_KNN_SCREEN_TC = 2, PROF_KNN_RERANK = 3, PROF_SLOTS = 8 };
+struct ProfScope {
+    ProfScope(int slot, cudaStream_t s);
+    ~ProfScope();
+    int slot_;
+    cudaStream_t s_;
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
 
 #define CLIBD_CHECK_CUDA(expr)                                                                    \
     do {                                                                                          \
@@ -35,7 +46,11 @@ void set_error(const std::string& msg);
         }                                                          \
     } while (0)
 
-#define CLIBD_KERNEL_CHECK() CLIBD_CHECK_CUDA(cudaGetLastError())
+#define CLIBD_KERNEL_CHECK()                   \
+    do {                                       \
+        ::clibd::count_launch();               \
+        CLIBD_CHECK_CUDA(cudaGetLastError());  \
+    } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -698,6 +698,8 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
     const int64_t units = ceil_div(Q, S_BM) * plan.num_chunks;
     const int grid = static_cast<int>(units < sm_count() ? units : sm_count());
     const uint32_t idesc = make_idesc_f16(S_BM, S_BN, fmt_bf16 ? 1u : 0u);
+    {
+    ProfScope prof(PROF_KNN_SCREEN_TC, stream);
     if (plan.kp == 8) {
         static bool attr8 = false;
         if (!attr8) {
@@ -715,6 +717,7 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
         knn_screen_tc_kernel<16><<<grid, S_THREADS, S_SMEM_ALLOC, stream>>>(tm_q, tm_k, Q, K, static_cast<int>(plan.dpad / S_BK),
                                                                             plan.num_chunks, plan.tiles_per_chunk, idesc, cs, ci);
     }
+    }
     CLIBD_KERNEL_CHECK();
     // rigorous bound on |screened - exact| for unit-norm rows: operand rounding (2u + u^2) with
     // u = 2^-11 (f16) or 2^-8 (bf16), f16 subnormal flush (<= 2 * sqrt(d) * 2^-25), and fp32
@@ -727,9 +730,12 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
     const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t)) + sizeof(float) * R_DC +
                            sizeof(float) * R_THREADS * (R_DC + 1);
     CLIBD_REQUIRE(rr_smem <= 48 * 1024, "too many candidate lists for the re-rank kernel");
+    {
+    ProfScope prof(PROF_KNN_RERANK, stream);
     knn_rerank_kernel<<<static_cast<unsigned>(Q), R_THREADS, rr_smem, stream>>>(
         q32, keys32, Q, K, d, k, plan.kp, plan.num_lists, static_cast<float>(eps), key_offset, cs, ci, out_sims64, out_idx,
         flagged, nflag);
+    }
     CLIBD_KERNEL_CHECK();
     int32_t h_nflag = 0;
     CLIBD_CHECK_CUDA(cudaMemcpyAsync(&h_nflag, nflag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));

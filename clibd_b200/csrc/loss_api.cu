@@ -1,5 +1,9 @@
 // extern "C" entry points of the contrastive-loss path (see include/clibd_b200.h).
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/clibd_b200.h"
 #include "common.cuh"
@@ -10,6 +14,26 @@ namespace clibd {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[PROF_SLOTS];
+
+ProfScope::ProfScope(int slot, cudaStream_t s) : slot_(slot), s_(s) {
+    if (!g_prof_on) return;
+    cudaEventCreate(&e0_);
+    cudaEventCreate(&e1_);
+    cudaEventRecord(e0_, s_);
+}
+ProfScope::~ProfScope() {
+    if (e0_ == nullptr) return;
+    cudaEventRecord(e1_, s_);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_events[slot_].emplace_back(e0_, e1_);
+}
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -94,6 +118,33 @@ extern "C" {
 int clibd_abi_version(void) { return CLIBD_ABI_VERSION; }
 
 const char* clibd_last_error(void) { return last_error().c_str(); }
+
+int64_t clibd_kernel_launch_count(void) { return g_launches.load(); }
+
+int clibd_profile_enable(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = enable != 0;
+    return 0;
+}
+
+int clibd_profile_read(double* total_ms, int64_t* launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int sl = 0; sl < PROF_SLOTS; ++sl) {
+        double ms = 0.0;
+        for (auto& ev : g_prof_events[sl]) {
+            cudaEventSynchronize(ev.second);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev.first, ev.second);
+            ms += t;
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        total_ms[sl] = ms;
+        launches[sl] = static_cast<int64_t>(g_prof_events[sl].size());
+        g_prof_events[sl].clear();
+    }
+    return 0;
+}
 
 int clibd_device_supported(void) {
     int dev = 0;

@@ -541,6 +541,7 @@ int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad,
     const int64_t tiles = ceil_div(n, FWD_BM) * ceil_div(N, FWD_BN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     const uint32_t idesc = make_idesc_f16(FWD_BM, FWD_BN, fmt_bf16 ? 1u : 0u);
+    ProfScope prof(PROF_LOSS_FWD_TC, s);
     loss_fwd_tc_kernel<<<grid, F_THREADS, F_SMEM_ALLOC, s>>>(tm_a, tm_b, N, row0, n, static_cast<int>(dpad / F_BK), scale,
                                                             idesc, rowpart, colpart);
     CLIBD_KERNEL_CHECK();
@@ -586,6 +587,7 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
                                     dpad - dc0 * BWD_DCH, npad, npad, B_BK, chunk_w / 2, fmt_bf16);
             if (rc) return rc;
         }
+        ProfScope prof(PROF_LOSS_BWD_TC, s);
         loss_bwd_tc_kernel<<<grid, B_THREADS, B_SMEM_ALLOC, s>>>(
             tm_x, tm_y, tm_yt_pass, N, d, d - dc0 * BWD_DCH, row0, n, static_cast<int>(dpad / B_BK), chunk_w,
             tiles_per_split, scale, idesc_s, idesc_g, fmt_bf16, rowcoef, colcoef, gscale, weight, accumulate,

@@ -221,7 +221,8 @@ def _fused_loss(image_features, dna_features, text_features, labels, logit_scale
     if n_ordered == 0:
         raise ZeroDivisionError("float division by zero")  # reference: sum([]) * 1.0 / len([])
     scale_tensor = logit_scale if isinstance(logit_scale, torch.Tensor) else None
-    scale_value = float(logit_scale)  # one host read when the scale is a tensor (the reference reads loss.item())
+    # one host read when the scale is a tensor (the reference reads loss.item() every step anyway)
+    scale_value = float(logit_scale.detach()) if scale_tensor is not None else float(logit_scale)
     path = _select_path(common, operands)
     return _FusedClipLossFn.apply(feats[0], feats[1], feats[2], labels, scale_tensor, scale_value, weights, path,
                                   group, world, rank, sum_grads)

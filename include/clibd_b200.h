@@ -36,6 +36,16 @@ const char* clibd_last_error(void);
 /* 1 if the current device is compute capability 10.x (the tcgen05 paths need it). */
 int clibd_device_supported(void);
 
+/* ---- telemetry (new; no reference counterpart) --------------------------------------
+ * Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t clibd_kernel_launch_count(void);
+/* Optional CUDA-event timing of the tensor-core kernels, recorded on their launching stream.
+ * Slots: 0 loss forward (tcgen05), 1 loss backward (tcgen05), 2 kNN screen (tcgen05), 3 kNN re-rank.
+ * clibd_profile_read synchronises the recorded events, writes per-slot total milliseconds and launch
+ * counts into host arrays of 8 entries each, and clears them. */
+int clibd_profile_enable(int enable);
+int clibd_profile_read(double* total_ms /* host [8] */, int64_t* launches /* host [8] */);
+
 /* ---- contrastive loss ------------------------------------------------------------
  * Replaces ContrastiveLoss.forward / ClipLoss.forward and their autograd backward
  * (bioscanclip/model/loss_func.py:41-69, :138-201) and construct_label_metrix (:19-22).

@@ -205,3 +205,33 @@ def clip_loss_rank(features_per_rank, labels_per_rank, rank, logit_scale, bind_t
     grads = [None if g is None else gsum * g[lo:hi] for g in res["grads"]]
     return {"loss": res["loss"], "grads": grads,
             "dlogit_scale": grad_out_per_rank[rank] * res["dlogit_scale"]}
+
+
+def row_block_fwd_bwd(features, labels, logit_scale, r0, r1, dtype=np.float32):
+    """One bounded SAMPLE of the full-batch step, used as the CPU baseline by bench.py: forward
+    statistics and backward products of rows [r0, r1) against all N columns for every unordered
+    modality pair (same math as contrastive_loss_streaming, one row block).  The full step costs
+    N / (r1 - r0) such blocks.  Returns the block's partial loss terms so the work cannot be elided."""
+    feats = [np.asarray(f, dtype=dtype) for f in features if f is not None]
+    N = feats[0].shape[0]
+    labels = np.asarray(labels)
+    s = dtype(logit_scale)
+    xh = [l2_normalize(f)[0] for f in feats]
+    _, inv, cnt = np.unique(labels, return_inverse=True, return_counts=True)
+    c = cnt[inv].astype(dtype)
+    acc = 0.0
+    for a in range(len(xh)):
+        for b in range(a + 1, len(xh)):
+            A, B = xh[a][r0:r1], xh[b]
+            cos = A @ B.T
+            E = np.exp(s * cos - s)
+            rs = E.sum(axis=1)
+            cs = E.sum(axis=0)  # partial column sums of this block
+            Tb = labels[r0:r1, None] == labels[None, :]
+            acc += float((c[r0:r1] * np.log(rs)).sum()) - float(cos[Tb].sum())
+            G = E * ((c[r0:r1] / rs)[:, None] + (c / np.maximum(cs * (N / (r1 - r0)), 1e-30))[None, :])
+            G -= 2.0 * Tb
+            dA = G @ B
+            dB = G.T @ A
+            acc += float(dA[0, 0]) + float(dB[0, 0])
+    return acc
