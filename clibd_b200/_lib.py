@@ -38,6 +38,18 @@ SIGNATURES = {
 }
 
 _lib = None
+_test_double = None
+
+
+def inject_for_tests(double):
+    """tests/ only: replace the CUDA library by an object with the same entry points so the host-side
+    collective choreography can be exercised under gloo on a CPU box.  Never set by product code."""
+    global _test_double
+    _test_double = double
+
+
+def test_double_active() -> bool:
+    return _test_double is not None
 
 
 def lib_path() -> str:
@@ -47,6 +59,8 @@ def lib_path() -> str:
 def load():
     """Load (building first if the sources are newer) the shared library."""
     global _lib
+    if _test_double is not None:
+        return _test_double
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
@@ -65,7 +79,8 @@ def load():
 
 def check(rc: int):
     if rc != 0:
-        msg = load().clibd_last_error().decode()
+        msg = load().clibd_last_error()
+        msg = msg.decode() if isinstance(msg, bytes) else str(msg)
         if rc == 1:
             raise ValueError("clibd_b200: " + msg)
         raise RuntimeError("clibd_b200: " + msg)

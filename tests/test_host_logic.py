@@ -1,0 +1,143 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), the pair-weight logic matches the reference's pair loop, and the
+multi-rank orchestration of ClipLoss reproduces the reference's world-2 golden vectors under gloo
+(with a numpy double standing in for the CUDA entry points)."""
+import itertools
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import loss_oracle as lo
+from tests import _golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from clibd_b200 import _build, _lib
+    header = open(os.path.join(ROOT, "include", "clibd_b200.h")).read()
+    declared = set(re.findall(r"\b(clibd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # builds if needed, dlopens, binds every symbol
+    assert os.path.exists(_build.LIB_PATH)
+    assert lib.clibd_abi_version() == 1
+    assert lib.clibd_loss_scratch_bytes(4096, 512, 768, 1) > 0
+    assert lib.clibd_loss_scratch_bytes(0, 0, 768, 1) == -1
+    assert lib.clibd_knn_scratch_bytes(1000, 100000, 768, 5, 2) > 0
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "clibd_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.parametrize("present", [p for p in itertools.product([0, 1], repeat=3) if sum(p) >= 2])
+@pytest.mark.parametrize("bind_to", [None, "image", "dna", "text"])
+@pytest.mark.parametrize("no_it", [False, True])
+def test_pair_weights_match_reference_pair_loop(present, bind_to, no_it):
+    from clibd_b200.loss import pair_weights
+    w, n_ordered = pair_weights(present, bind_to, no_it)
+    pairs = lo.ordered_pairs(sum(present), bind_to, no_it)
+    assert n_ordered == len(pairs)
+    slots = [i for i, p in enumerate(present) if p]
+    expect = [0.0, 0.0, 0.0]
+    idx = {(0, 1): 0, (0, 2): 1, (1, 2): 2}
+    for a, b in pairs:
+        key = (min(slots[a], slots[b]), max(slots[a], slots[b]))
+        expect[idx[key]] += 1.0 / (2 * len(pairs))
+    assert w == pytest.approx(expect)
+
+
+def test_reference_argument_errors_without_gpu():
+    import clibd_b200 as cb
+    x = torch.randn(4, 8)
+    with pytest.raises(ValueError, match="Too less element"):
+        cb.ContrastiveLoss(torch.nn.CrossEntropyLoss(), 1.0)(x, None, None, torch.arange(4), 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cb.ContrastiveLoss(torch.nn.CrossEntropyLoss(), 1.0)(x, x, None, torch.arange(4), 1.0)
+    with pytest.raises(NotImplementedError):
+        cb.ClipLoss(use_horovod=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA device"):
+            cb.make_prediction(np.zeros((2, 4)), np.zeros((3, 4)), [{}] * 3)
+
+
+def test_single_process_orchestration_with_double_matches_golden():
+    from clibd_b200 import _lib
+    import clibd_b200 as cb
+    from tests._fake_lib import FakeLib
+    _lib.inject_for_tests(FakeLib())
+    try:
+        for g in _golden.all_single_process():
+            if g.meta.get("inputs_are_bf16_exact"):
+                continue
+            feats = [None if f is None else torch.from_numpy(f).requires_grad_(True) for f in g.features]
+            mod = cb.ClipLoss(gather_with_grad=True, **g.kwargs())
+            scale = torch.tensor(g.logit_scale, requires_grad=True)
+            loss = mod(feats[0], feats[1], feats[2], torch.from_numpy(g.labels), scale)
+            (loss * g.meta.get("grad_mult", 1.0)).backward()
+            assert float(loss) == pytest.approx(float(g.outputs["loss"]), rel=2e-6)
+            for f, m in zip(feats, _golden.MODS):
+                if f is not None:
+                    ref = g.outputs[f"grad_{m}"]
+                    assert np.linalg.norm(f.grad.numpy() - ref) / np.linalg.norm(ref) < 2e-5
+            if "dlogit_scale" in g.outputs:
+                assert float(scale.grad) == pytest.approx(float(g.outputs["dlogit_scale"]), rel=2e-4, abs=1e-7)
+    finally:
+        _lib.inject_for_tests(None)
+
+
+def _w2_worker(rank, world, store, ret):
+    from clibd_b200 import _lib
+    import clibd_b200 as cb
+    from tests._fake_lib import FakeLib
+    dist.init_process_group("gloo", init_method=f"file://{store}", rank=rank, world_size=world)
+    _lib.inject_for_tests(FakeLib())
+    g = _golden.load("cliploss_w2_all_n64_d32")
+    n = 32
+    sl = slice(rank * n, (rank + 1) * n)
+    feats = [torch.from_numpy(g.inputs[m][sl].copy()).requires_grad_(True) for m in _golden.MODS]
+    scale = torch.tensor(g.logit_scale, requires_grad=True)
+    mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world)
+    loss = mod(feats[0], feats[1], feats[2], torch.from_numpy(g.labels[sl].copy()), scale)
+    loss.backward()
+    out = {"loss": float(loss), "ds": float(scale.grad)}
+    for f, m in zip(feats, _golden.MODS):
+        out[m] = f.grad.numpy().tolist()
+    # gather_with_grad=False: only this rank's loss reaches the local rows (no sum over ranks)
+    feats2 = [torch.from_numpy(g.inputs[m][sl].copy()).requires_grad_(True) for m in _golden.MODS]
+    mod2 = cb.ClipLoss(local_loss=False, gather_with_grad=False, rank=rank, world_size=world)
+    mod2(feats2[0], feats2[1], feats2[2], torch.from_numpy(g.labels[sl].copy()), g.logit_scale).backward()
+    out["image_nograd_gather"] = feats2[0].grad.numpy().tolist()
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_orchestration_matches_reference_golden():
+    """The reference ran ClipLoss(gather_with_grad=True) under 2 gloo processes (oracle/gen_golden.py);
+    our orchestration (all-gather in, all-reduce of statistics, sum-over-ranks gradient scale) must give
+    every rank the same full-batch loss and W x the local slice of the full-batch gradient."""
+    world = 2
+    store = tempfile.mktemp()
+    ret = mp.Manager().dict()
+    mp.spawn(_w2_worker, args=(world, store, ret), nprocs=world, join=True)
+    g = _golden.load("cliploss_w2_all_n64_d32")
+    for r in range(world):
+        assert ret[r]["loss"] == pytest.approx(float(g.outputs[f"rank{r}_loss"]), rel=2e-6)
+        assert ret[r]["ds"] == pytest.approx(float(g.outputs[f"rank{r}_dlogit_scale"]), rel=2e-4)
+        for m in _golden.MODS:
+            ref = g.outputs[f"rank{r}_grad_{m}"]
+            got = np.asarray(ret[r][m], dtype=np.float32)
+            assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-5
+        half = np.asarray(ret[r]["image_nograd_gather"], dtype=np.float32)
+        ref = g.outputs[f"rank{r}_grad_image"] / world
+        assert np.linalg.norm(half - ref) / np.linalg.norm(ref) < 2e-5
