@@ -185,22 +185,40 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[as]);
                     }
-                    const int64_t cb = colbase + c * 32;
+                    const int32_t cb = static_cast<int32_t>(colbase) + c * 32;
+                    float f[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        float s = __uint_as_float(v[k]);
-                        if (!full_tile && cb + k >= K) s = -INFINITY;
-                        if (s > ls[KP - 1]) {  // strict: an equal score with a higher index never displaces
-                            int32_t id = static_cast<int32_t>(cb + k);
+                    for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+                    if (!full_tile) {
+                        const int32_t kvalid = static_cast<int32_t>(K) - cb;  // columns >= kvalid do not exist
 #pragma unroll
-                            for (int i = 0; i < KP; ++i) {
-                                if (s > ls[i]) {
-                                    const float ts = ls[i];
-                                    const int32_t ti = li[i];
-                                    ls[i] = s;
-                                    li[i] = id;
-                                    s = ts;
-                                    id = ti;
+                        for (int k = 0; k < 32; ++k)
+                            if (k >= kvalid) f[k] = -INFINITY;
+                    }
+                    // one branch per 32 columns: most chunks hold nothing above the list's last entry
+                    float m01[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) m01[k] = fmaxf(f[2 * k], f[2 * k + 1]);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int k = 0; k < w; ++k) m01[k] = fmaxf(m01[k], m01[k + w]);
+                    if (m01[0] > ls[KP - 1]) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            float s = f[k];
+                            if (s > ls[KP - 1]) {  // strict: an equal score with a higher index never displaces
+                                int32_t id = cb + k;
+#pragma unroll
+                                for (int i = 0; i < KP; ++i) {
+                                    if (s > ls[i]) {
+                                        const float ts = ls[i];
+                                        const int32_t ti = li[i];
+                                        ls[i] = s;
+                                        li[i] = id;
+                                        s = ts;
+                                        id = ti;
+                                    }
                                 }
                             }
                         }
@@ -230,7 +248,6 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 // exact re-rank of the screened candidates; one block (64 threads) per query
 // ------------------------------------------------------------------------------------------
 constexpr int R_THREADS = 64;
-constexpr int R_DC = 128;
 
 __global__ void __launch_bounds__(R_THREADS)
 knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, int64_t Q, int64_t K, int64_t d,
@@ -241,8 +258,7 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     const int C = num_lists * kp;
     double* sims = reinterpret_cast<double*>(rr_smem);                 // [C]
     int32_t* ids = reinterpret_cast<int32_t*>(sims + C);               // [C]
-    float* qs = reinterpret_cast<float*>(ids + C);                     // [R_DC]
-    float* tile = qs + R_DC;                                           // [64][R_DC + 1]
+    float* qs = reinterpret_cast<float*>(ids + C);                     // [d]
     __shared__ double s_best[2];
     __shared__ int s_besti[2];
     __shared__ int s_bestc[2];
@@ -250,27 +266,30 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     const int tid = threadIdx.x;
     const float* qrow = q32 + qi * d;
     for (int c = tid; c < C; c += R_THREADS) ids[c] = cand_idx[qi * C + c];
+    for (int64_t t = tid; t < d; t += R_THREADS) qs[t] = qrow[t];
     __syncthreads();
-    for (int c0 = 0; c0 < C; c0 += R_THREADS) {
-        const int c = c0 + tid;
-        const int myid = (c < C) ? ids[c] : -1;
+    // one candidate per thread: float64 accumulation over d in index order (the oracle's order);
+    // a thread streams its own key row, 16 bytes at a time (lines stay in L1 between the 8 visits)
+    const bool vec4 = (d % 4 == 0);
+    for (int c = tid; c < C; c += R_THREADS) {
+        const int myid = ids[c];
         double acc = 0.0;
-        for (int64_t d0 = 0; d0 < d; d0 += R_DC) {
-            const int dl = static_cast<int>(min(static_cast<int64_t>(R_DC), d - d0));
-            for (int t = tid; t < dl; t += R_THREADS) qs[t] = qrow[d0 + t];
-            for (int r = 0; r < R_THREADS; ++r) {  // coalesced row segments
-                const int cid = (c0 + r < C) ? ids[c0 + r] : -1;
-                for (int t = tid; t < dl; t += R_THREADS)
-                    tile[r * (R_DC + 1) + t] = (cid >= 0) ? k32[static_cast<int64_t>(cid) * d + d0 + t] : 0.f;
+        if (myid >= 0) {
+            const float* kr = k32 + static_cast<int64_t>(myid) * d;
+            if (vec4) {
+                const float4* kr4 = reinterpret_cast<const float4*>(kr);
+                for (int64_t t = 0; t < d / 4; ++t) {
+                    const float4 kv = __ldg(kr4 + t);
+                    acc += static_cast<double>(qs[4 * t]) * static_cast<double>(kv.x);
+                    acc += static_cast<double>(qs[4 * t + 1]) * static_cast<double>(kv.y);
+                    acc += static_cast<double>(qs[4 * t + 2]) * static_cast<double>(kv.z);
+                    acc += static_cast<double>(qs[4 * t + 3]) * static_cast<double>(kv.w);
+                }
+            } else {
+                for (int64_t t = 0; t < d; ++t) acc += static_cast<double>(qs[t]) * static_cast<double>(__ldg(kr + t));
             }
-            __syncthreads();
-            if (myid >= 0) {
-                const float* tr = tile + tid * (R_DC + 1);
-                for (int t = 0; t < dl; ++t) acc += static_cast<double>(qs[t]) * static_cast<double>(tr[t]);
-            }
-            __syncthreads();
         }
-        if (c < C) sims[c] = (myid >= 0) ? acc : -DBL_MAX;
+        sims[c] = (myid >= 0) ? acc : -DBL_MAX;
     }
     __syncthreads();
     // k rounds of arg-best by (-sim, index)
@@ -727,8 +746,7 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
                        static_cast<double>(d) * 2.384185791015625e-07;
     CLIBD_CHECK_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int32_t) * 4, stream));
     const int C = plan.num_lists * plan.kp;
-    const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t)) + sizeof(float) * R_DC +
-                           sizeof(float) * R_THREADS * (R_DC + 1);
+    const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t)) + sizeof(float) * d;
     CLIBD_REQUIRE(rr_smem <= 48 * 1024, "too many candidate lists for the re-rank kernel");
     {
     ProfScope prof(PROF_KNN_RERANK, stream);

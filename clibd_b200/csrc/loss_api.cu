@@ -49,12 +49,19 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
     if (tc) {
         p.row_parts = ceil_div(N, FWD_BN);
         p.col_parts = ceil_div(n, FWD_BM);
+        // split the column sweep so that the CTA count fills whole waves of 148 SMs (1 CTA / SM)
         const int64_t ctas = ceil_div(n, BWD_BM) * ceil_div(p.dpad, BWD_DCH);
-        int64_t js = ceil_div(2 * 148, ctas > 0 ? ctas : 1);
         const int64_t num_jt = ceil_div(N, BWD_BJ);
-        if (js > 8) js = 8;
-        if (js > num_jt) js = num_jt;
-        if (js < 1) js = 1;
+        int64_t js = 1;
+        double best = 0.0;
+        for (int64_t c = 1; c <= 8 && c <= num_jt; ++c) {
+            const int64_t total = ctas * c;
+            const double eff = static_cast<double>(total) / static_cast<double>(ceil_div(total, 148) * 148);
+            if (eff > best + 0.02) {
+                best = eff;
+                js = c;
+            }
+        }
         p.jsplit = static_cast<int>(js);
     } else {
         p.row_parts = ceil_div(N, SIMT_T);

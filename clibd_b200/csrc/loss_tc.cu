@@ -17,6 +17,8 @@
 //   swizzled into shared memory as the A operand -> dXhat += G~ * Yhat (B operand from the
 //   transposed 16-bit copy so that every operand is K-major).  The label-matched "-2 T" term
 //   is not in this kernel: it is a class-sum of O(N d) done in loss_support.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_plan.h"
 #include "ptx.cuh"
@@ -101,54 +103,58 @@ loss_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // Producer and MMA warps stay converged (all 32 lanes walk the loops, one elected lane issues):
+    // loop state then lives in uniform registers, which is what UTMALDG / UTCHMMA take as operands.
+    const uint32_t smem_base = smem_u32(smem);
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int64_t mt, nt;
-                tile_coords(t, num_mt, num_nt, mt, nt);
-                const int32_t arow = static_cast<int32_t>(row0 + mt * FWD_BM);
-                const int32_t brow = static_cast<int32_t>(nt * FWD_BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int64_t mt, nt;
+            tile_coords(t, num_mt, num_nt, mt, nt);
+            const int32_t arow = static_cast<int32_t>(row0 + mt * FWD_BM);
+            const int32_t brow = static_cast<int32_t>(nt * FWD_BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem + stage * F_STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], F_STAGE_BYTES);
                     tma_load_2d(&tm_a, &full_bar[stage], sa, kb * F_BK, arow, kEvictNormal);
                     tma_load_2d(&tm_b, &full_bar[stage], sa + F_A_BYTES, kb * F_BK, brow, kEvictNormal);
-                    if (++stage == F_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == F_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const uint32_t as = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aph ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * FWD_BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * FWD_BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * F_STAGE_BYTES);
-                    const uint64_t da = make_sw128_kmajor_desc(sa);
-                    const uint64_t db = make_sw128_kmajor_desc(sa + F_A_BYTES);
+                const uint32_t sa = smem_base + stage * F_STAGE_BYTES;
+                const uint64_t da = make_sw128_kmajor_desc(sa);
+                const uint64_t db = make_sw128_kmajor_desc(sa + F_A_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < F_BK / 16; ++k)
-                        umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc,
-                                 (kb | k) ? 1u : 0u);
+                        umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
-                    if (++stage == F_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == F_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
@@ -237,48 +243,47 @@ loss_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------
-constexpr int B_SSTAGES = 3;
 constexpr int B_BK = 64;
-constexpr int B_X_BYTES = BWD_BM * B_BK * 2;         // 16 KB
-constexpr int B_Y_BYTES = BWD_BJ * B_BK * 2;         // 16 KB
-constexpr int B_SSTAGE_BYTES = B_X_BYTES + B_Y_BYTES;
-constexpr int B_G_BYTES = BWD_BM * BWD_BJ * 2;       // 32 KB (two 64-wide K blocks)
-constexpr int B_YTSTAGES = 4;
-constexpr int B_YT_BYTES = (BWD_DCH / 2) * B_BK * 2;  // 24 KB
+constexpr int B_TILE_BYTES = 128 * B_BK * 2;          // 16 KB: a 128-row x 64-column 16-bit operand tile
+constexpr int B_STAGE_BYTES = 4 * B_TILE_BYTES;       // 64 KB: two K blocks of X and of Y, or the YhatT tiles of one K block
+constexpr int B_STAGES = 3;                           // 192 KB of operands in flight
+constexpr int B_G_BYTES = BWD_BM * BWD_BJ * 2;        // 32 KB (two 64-wide K blocks)
 constexpr int B_THREADS = 256;
-constexpr int B_SMEM_G = B_SSTAGES * B_SSTAGE_BYTES;
-constexpr int B_SMEM_YT = B_SMEM_G + B_G_BYTES;
-constexpr int B_SMEM_CC = B_SMEM_YT + B_YTSTAGES * B_YT_BYTES;  // float [2][128]
+constexpr uint32_t B_TMEM_S_COL = 384;
+constexpr int B_SMEM_G = B_STAGES * B_STAGE_BYTES;
+constexpr int B_SMEM_CC = B_SMEM_G + B_G_BYTES;       // float [2][128]
 constexpr int B_SMEM_BARS = B_SMEM_CC + 2 * BWD_BJ * 4;
-constexpr int B_NUM_BARS = 2 * B_SSTAGES + 2 * B_YTSTAGES + 5;
+constexpr int B_NUM_BARS = 2 * B_STAGES + 5;
 constexpr int B_SMEM_TMEMPTR = B_SMEM_BARS + B_NUM_BARS * 8;
 constexpr int B_SMEM_TOTAL = B_SMEM_TMEMPTR + 16;
 constexpr int B_SMEM_ALLOC = B_SMEM_TOTAL + 1024;
-constexpr uint32_t B_TMEM_S_COL = 384;
 static_assert(B_SMEM_ALLOC <= 232448, "backward kernel shared memory exceeds 227 KB");
 static_assert(F_SMEM_ALLOC <= 232448, "forward kernel shared memory exceeds 227 KB");
 
+// One ring of three 64 KB stages serves both GEMMs; the producer warp and the MMA warp walk the SAME
+// stage sequence:   for each column tile t:  ceil(num_kb/2) S stages  (X k, X k+1, Y k, Y k+1 : 8 MMAs)
+//                   then, for tile t-1:      2 gradient stages        (the YhatT pieces of one K block)
+// Few, fat stages matter: issuing is paced by one mbarrier wait + one commit per stage, and with
+// N=128 an MMA lasts only 64 cycles, so 4-MMA stages left the tensor pipe waiting on the issuer.
 __global__ void __launch_bounds__(B_THREADS, 1)
 loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                    const __grid_constant__ CUtensorMap tm_yt, int64_t N, int64_t ld, int64_t dvalid, int64_t row0,
-                   int64_t n, int num_kb, int chunk_w, int64_t tiles_per_split, float scale, uint32_t idesc_s, uint32_t idesc_g,
-                   int fmt_bf16, const float* __restrict__ rowcoef, const float* __restrict__ colcoef,
-                   const float* __restrict__ gscale, float weight, int accumulate, float* __restrict__ dxh) {
+                   int64_t n, int num_kb, int chunk_w, int npieces, int64_t tiles_per_split, float scale,
+                   uint32_t idesc_s, uint32_t idesc_g, int fmt_bf16, const float* __restrict__ rowcoef,
+                   const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
+                   float* __restrict__ dxh) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* gbuf = smem + B_SMEM_G;
-    uint8_t* ytbuf = smem + B_SMEM_YT;
     float* ccbuf = reinterpret_cast<float*>(smem + B_SMEM_CC);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_SMEM_BARS);
-    uint64_t* sfull = bars;
-    uint64_t* sempty = bars + B_SSTAGES;
-    uint64_t* ytfull = bars + 2 * B_SSTAGES;
-    uint64_t* ytempty = ytfull + B_YTSTAGES;
-    uint64_t* st_full = ytempty + B_YTSTAGES;  // S tile ready in TMEM
-    uint64_t* st_empty = st_full + 1;          // S tile drained by the epilogue
-    uint64_t* g_full = st_full + 2;            // G~ tile written to smem
-    uint64_t* g_empty = st_full + 3;           // G~ tile consumed by the MMA
-    uint64_t* acc_full = st_full + 4;          // all accumulation finished
+    uint64_t* full = bars;
+    uint64_t* empty = bars + B_STAGES;
+    uint64_t* st_full = bars + 2 * B_STAGES;  // S tile ready in TMEM
+    uint64_t* st_empty = st_full + 1;         // S tile drained by the epilogue
+    uint64_t* g_full = st_full + 2;           // G~ tile written to smem
+    uint64_t* g_empty = st_full + 3;          // G~ tile consumed by the MMA
+    uint64_t* acc_full = st_full + 4;         // all accumulation finished
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + B_SMEM_TMEMPTR);
 
     const int warp = threadIdx.x >> 5;
@@ -289,20 +294,17 @@ loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int64_t num_jt = (N + BWD_BJ - 1) / BWD_BJ;
     const int64_t jt0 = split * tiles_per_split;
     const int64_t jt1 = (jt0 + tiles_per_split < num_jt) ? (jt0 + tiles_per_split) : num_jt;
-    const int half_w = chunk_w / 2;
-    const uint32_t yt_bytes = static_cast<uint32_t>(half_w) * B_BK * 2;
+    const int piece_w = chunk_w / npieces;                       // accumulator columns per gradient MMA
+    const uint32_t piece_bytes = static_cast<uint32_t>(piece_w) * B_BK * 2;
+    const int num_sst = (num_kb + 1) / 2;                        // S stages per column tile
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_x);
         prefetch_tmap(&tm_y);
         prefetch_tmap(&tm_yt);
-        for (int i = 0; i < B_SSTAGES; ++i) {
-            mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 1);
-        }
-        for (int i = 0; i < B_YTSTAGES; ++i) {
-            mbar_init(&ytfull[i], 1);
-            mbar_init(&ytempty[i], 1);
+        for (int i = 0; i < B_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
         }
         mbar_init(st_full, 1);
         mbar_init(st_empty, 4);
@@ -319,102 +321,117 @@ loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t smem_base = smem_u32(smem);
 
     if (jt0 < jt1) {
-        if (warp == 0) {
-            if (lane == 0) {  // producer of the S-GEMM operands
-                int stage = 0;
-                uint32_t phase = 0;
-                const int32_t xrow = static_cast<int32_t>(row0 + mt * BWD_BM);
-                for (int64_t t = jt0; t < jt1; ++t) {
-                    const int32_t yrow = static_cast<int32_t>(t * BWD_BJ);
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&sempty[stage], phase ^ 1);
-                        uint8_t* sx = smem + stage * B_SSTAGE_BYTES;
-                        mbar_arrive_expect_tx(&sfull[stage], B_SSTAGE_BYTES);
-                        tma_load_2d(&tm_x, &sfull[stage], sx, kb * B_BK, xrow, kEvictNormal);
-                        tma_load_2d(&tm_y, &sfull[stage], sx + B_X_BYTES, kb * B_BK, yrow, kEvictNormal);
-                        if (++stage == B_SSTAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
+        if (warp == 0) {  // producer warp (converged; one elected lane issues)
+            int stage = 0;
+            uint32_t phase = 0;
+            const int32_t xrow = static_cast<int32_t>(row0 + mt * BWD_BM);
+            auto advance = [&]() {
+                if (++stage == B_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
-            }
-        } else if (warp == 3) {
-            if (lane == 0) {  // producer of the transposed Yhat tiles for the gradient GEMM
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int64_t t = jt0; t < jt1; ++t) {
-                    for (int kb2 = 0; kb2 < BWD_BJ / B_BK; ++kb2) {
-                        for (int hf = 0; hf < 2; ++hf) {
-                            mbar_wait(&ytempty[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&ytfull[stage], yt_bytes);
-                            tma_load_2d(&tm_yt, &ytfull[stage], ytbuf + stage * B_YT_BYTES,
+            };
+            auto load_grad = [&](int64_t t) {
+                for (int kb2 = 0; kb2 < BWD_BJ / B_BK; ++kb2) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        uint8_t* sb = smem + stage * B_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], piece_bytes * npieces);
+                        for (int pc = 0; pc < npieces; ++pc)
+                            tma_load_2d(&tm_yt, &full[stage], sb + pc * piece_bytes,
                                         static_cast<int32_t>(t * BWD_BJ + kb2 * B_BK),
-                                        static_cast<int32_t>(dc * BWD_DCH + hf * half_w), kEvictNormal);
-                            if (++stage == B_YTSTAGES) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
+                                        static_cast<int32_t>(dc * BWD_DCH + pc * piece_w), kEvictNormal);
+                    }
+                    __syncwarp();
+                    advance();
+                }
+            };
+            for (int64_t t = jt0; t < jt1; ++t) {
+                const int32_t yrow = static_cast<int32_t>(t * BWD_BJ);
+                for (int ss = 0; ss < num_sst; ++ss) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        uint8_t* sb = smem + stage * B_STAGE_BYTES;
+                        const int nkk = (num_kb - 2 * ss) < 2 ? (num_kb - 2 * ss) : 2;
+                        mbar_arrive_expect_tx(&full[stage], nkk * 2 * B_TILE_BYTES);
+                        for (int kk = 0; kk < nkk; ++kk) {
+                            tma_load_2d(&tm_x, &full[stage], sb + kk * B_TILE_BYTES, (2 * ss + kk) * B_BK, xrow, kEvictNormal);
+                            tma_load_2d(&tm_y, &full[stage], sb + (2 + kk) * B_TILE_BYTES, (2 * ss + kk) * B_BK, yrow,
+                                        kEvictNormal);
                         }
                     }
+                    __syncwarp();
+                    advance();
                 }
+                if (t > jt0) load_grad(t - 1);
             }
-        } else if (warp == 1) {
-            if (lane == 0) {  // MMA issuer
-                int stage = 0, ystage = 0;
-                uint32_t phase = 0, yphase = 0;
-                const uint32_t s_tmem = tmem_base + B_TMEM_S_COL;
-                const uint32_t gaddr = smem_u32(gbuf);
-                auto issue_grad = [&](int64_t tl) {  // tl = t - jt0 of the G~ tile to consume
-                    mbar_wait(g_full, tl & 1);
+            load_grad(jt1 - 1);
+        } else if (warp == 1) {  // MMA warp (converged; one elected lane issues)
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t s_tmem = tmem_base + B_TMEM_S_COL;
+            const uint32_t gaddr = smem_u32(gbuf);
+            auto advance = [&]() {
+                if (++stage == B_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            auto issue_grad = [&](int64_t tl) {  // tl = t - jt0 of the G~ tile to consume
+                mbar_wait(g_full, tl & 1);
+                tc_fence_after();
+                for (int kb2 = 0; kb2 < BWD_BJ / B_BK; ++kb2) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    for (int kb2 = 0; kb2 < BWD_BJ / B_BK; ++kb2) {
-                        const uint64_t da = make_sw128_kmajor_desc(gaddr + kb2 * (BWD_BM * 128));
-                        for (int hf = 0; hf < 2; ++hf) {
-                            mbar_wait(&ytfull[ystage], yphase);
-                            tc_fence_after();
-                            const uint64_t db = make_sw128_kmajor_desc(smem_u32(ytbuf + ystage * B_YT_BYTES));
+                    const uint64_t da = make_sw128_kmajor_desc(gaddr + kb2 * (BWD_BM * 128));
+                    const uint32_t sb = smem_base + stage * B_STAGE_BYTES;
+                    if (elect_one()) {
+                        for (int pc = 0; pc < npieces; ++pc) {
+                            const uint64_t db = make_sw128_kmajor_desc(sb + pc * piece_bytes);
 #pragma unroll
                             for (int k = 0; k < B_BK / 16; ++k)
-                                umma_f16(tmem_base + hf * half_w, desc_advance(da, k * 32), desc_advance(db, k * 32),
+                                umma_f16(tmem_base + pc * piece_w, desc_advance(da, k * 32), desc_advance(db, k * 32),
                                          idesc_g, (tl > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
-                            umma_commit(&ytempty[ystage]);
-                            if (++ystage == B_YTSTAGES) {
-                                ystage = 0;
-                                yphase ^= 1;
-                            }
                         }
+                        umma_commit(&empty[stage]);
+                        if (kb2 == BWD_BJ / B_BK - 1) umma_commit(g_empty);
                     }
-                    umma_commit(g_empty);
-                };
-                for (int64_t t = jt0; t < jt1; ++t) {
-                    const int64_t tl = t - jt0;
-                    mbar_wait(st_empty, (tl & 1) ^ 1);
-                    tc_fence_after();
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&sfull[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sx = smem_u32(smem + stage * B_SSTAGE_BYTES);
-                        const uint64_t da = make_sw128_kmajor_desc(sx);
-                        const uint64_t db = make_sw128_kmajor_desc(sx + B_X_BYTES);
-#pragma unroll
-                        for (int k = 0; k < B_BK / 16; ++k)
-                            umma_f16(s_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s,
-                                     (kb | k) ? 1u : 0u);
-                        umma_commit(&sempty[stage]);
-                        if (++stage == B_SSTAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                    umma_commit(st_full);
-                    if (tl > 0) issue_grad(tl - 1);
+                    __syncwarp();
+                    advance();
                 }
-                issue_grad(jt1 - jt0 - 1);
-                umma_commit(acc_full);
+            };
+            for (int64_t t = jt0; t < jt1; ++t) {
+                const int64_t tl = t - jt0;
+                mbar_wait(st_empty, (tl & 1) ^ 1);
+                tc_fence_after();
+                for (int ss = 0; ss < num_sst; ++ss) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_base + stage * B_STAGE_BYTES;
+                    const int nkk = (num_kb - 2 * ss) < 2 ? (num_kb - 2 * ss) : 2;
+                    if (elect_one()) {
+                        for (int kk = 0; kk < nkk; ++kk) {
+                            const uint64_t da = make_sw128_kmajor_desc(sb + kk * B_TILE_BYTES);
+                            const uint64_t db = make_sw128_kmajor_desc(sb + (2 + kk) * B_TILE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < B_BK / 16; ++k)
+                                umma_f16(s_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s,
+                                         (ss | kk | k) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (ss == num_sst - 1) umma_commit(st_full);
+                    }
+                    __syncwarp();
+                    advance();
+                }
+                if (tl > 0) issue_grad(tl - 1);
             }
+            issue_grad(jt1 - jt0 - 1);
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         } else if (warp >= 4) {
             const int q = warp & 3;
             const int etid = (warp - 4) * 32 + lane;  // == row of the tile
@@ -566,30 +583,27 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
     if (rc) return rc;
     const int64_t num_jt = ceil_div(N, BWD_BJ);
     const int64_t tiles_per_split = ceil_div(num_jt, jsplit);
-    // d chunks: full BWD_DCH-wide chunks, then one remainder chunk (multiple of 64)
+    const uint32_t idesc_s = make_idesc_f16(BWD_BM, BWD_BJ, fmt_bf16 ? 1u : 0u);
+    // d chunks: full BWD_DCH-wide chunks (grid.y), then one narrower remainder chunk (multiple of 64)
     const int64_t full_chunks = dpad / BWD_DCH;
     const int64_t rem = dpad % BWD_DCH;
     for (int pass = 0; pass < 2; ++pass) {
         const int64_t nch = pass == 0 ? full_chunks : (rem ? 1 : 0);
         if (nch == 0) continue;
         const int chunk_w = pass == 0 ? BWD_DCH : static_cast<int>(rem);
+        const int npieces = chunk_w > 256 ? 2 : 1;   // gradient MMA N = chunk_w / npieces (<= 256, multiple of 32)
+        const int piece_w = chunk_w / npieces;
         const int64_t dc0 = pass == 0 ? 0 : full_chunks;
-        rc = make_tmap_2d_16bit(&tm_yt, xhT_y, dpad, npad, npad, B_BK, chunk_w / 2, fmt_bf16);
-        if (rc) return rc;
-        const uint32_t idesc_s = make_idesc_f16(BWD_BM, BWD_BJ, fmt_bf16 ? 1u : 0u);
-        const uint32_t idesc_g = make_idesc_f16(BWD_BM, chunk_w / 2, fmt_bf16 ? 1u : 0u);
         dim3 grid(static_cast<unsigned>(ceil_div(n, BWD_BM)), static_cast<unsigned>(nch), static_cast<unsigned>(jsplit));
-        // blockIdx.y indexes the chunks of this pass; the remainder pass folds its chunk offset into
-        // the dxh pointer, the valid-column count and the base row of the transposed-operand map.
-        CUtensorMap tm_yt_pass = tm_yt;
-        if (dc0 > 0) {
-            rc = make_tmap_2d_16bit(&tm_yt_pass, static_cast<const uint16_t*>(xhT_y) + dc0 * BWD_DCH * npad,
-                                    dpad - dc0 * BWD_DCH, npad, npad, B_BK, chunk_w / 2, fmt_bf16);
-            if (rc) return rc;
-        }
+        // the remainder pass folds its chunk offset into the dxh pointer, the valid-column count and the
+        // base row of the transposed-operand map
+        rc = make_tmap_2d_16bit(&tm_yt, static_cast<const uint16_t*>(xhT_y) + dc0 * BWD_DCH * npad, dpad - dc0 * BWD_DCH,
+                                npad, npad, B_BK, piece_w, fmt_bf16);
+        if (rc) return rc;
+        const uint32_t idesc_g = make_idesc_f16(BWD_BM, piece_w, fmt_bf16 ? 1u : 0u);
         ProfScope prof(PROF_LOSS_BWD_TC, s);
         loss_bwd_tc_kernel<<<grid, B_THREADS, B_SMEM_ALLOC, s>>>(
-            tm_x, tm_y, tm_yt_pass, N, d, d - dc0 * BWD_DCH, row0, n, static_cast<int>(dpad / B_BK), chunk_w,
+            tm_x, tm_y, tm_yt, N, d, d - dc0 * BWD_DCH, row0, n, static_cast<int>(dpad / B_BK), chunk_w, npieces,
             tiles_per_split, scale, idesc_s, idesc_g, fmt_bf16, rowcoef, colcoef, gscale, weight, accumulate,
             dxh + dc0 * BWD_DCH);
         CLIBD_KERNEL_CHECK();
