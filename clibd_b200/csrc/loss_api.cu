@@ -1,5 +1,6 @@
 // extern "C" entry points of the contrastive-loss path (see include/clibd_b200.h).
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -49,14 +50,17 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
     if (tc) {
         p.row_parts = ceil_div(N, FWD_BN);
         p.col_parts = ceil_div(n, FWD_BM);
-        // split the column sweep so that the CTA count fills whole waves of 148 SMs (1 CTA / SM)
-        const int64_t ctas = ceil_div(n, BWD_BM) * ceil_div(p.dpad, BWD_DCH);
-        const int64_t num_jt = ceil_div(N, BWD_BJ);
+        // split the column sweep so that the work items fill whole waves (1 CTA / SM; the pair kernel runs
+        // 74 CTA pairs at once, the single-CTA kernel 148 CTAs of 384-wide chunks)
+        const bool pair = p.dpad <= PAIR_DCH;
+        const int64_t slots = pair ? PAIR_SLOTS : 148;
+        const int64_t ctas = pair ? ceil_div(n, PAIR_BM) : ceil_div(n, BWD_BM) * ceil_div(p.dpad, BWD_DCH);
+        const int64_t num_jt = pair ? ceil_div(N, PAIR_BJ) : ceil_div(N, BWD_BJ);
         int64_t js = 1;
         double best = 0.0;
         for (int64_t c = 1; c <= 8 && c <= num_jt; ++c) {
             const int64_t total = ctas * c;
-            const double eff = static_cast<double>(total) / static_cast<double>(ceil_div(total, 148) * 148);
+            const double eff = static_cast<double>(total) / static_cast<double>(ceil_div(total, slots) * slots);
             if (eff > best + 0.02) {
                 best = eff;
                 js = c;
@@ -286,7 +290,12 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
             } else {
                 continue;
             }
-            if (tc) {
+            if (tc && pair_backward_supported(plan.dpad) && !std::getenv("CLIBD_BWD_SINGLE")) {
+                rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xh[other]),
+                                           at<void>(scratch, plan.off_xhT[other]), N, plan.npad, d, plan.dpad, row0, n,
+                                           logit_scale, rowcoef, colcoef, gscale, pair_weight[p], npart > 0,
+                                           plan.jsplit, fmt_bf16, dxh, stream);
+            } else if (tc) {
                 rc = tc_backward_rows(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xh[other]),
                                       at<void>(scratch, plan.off_xhT[other]), N, plan.npad, d, plan.dpad, row0, n,
                                       logit_scale, rowcoef, colcoef, gscale, pair_weight[p], npart > 0, plan.jsplit,

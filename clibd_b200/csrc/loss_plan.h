@@ -13,6 +13,11 @@ constexpr int FWD_BN = 256;   // columns of S per CTA tile
 constexpr int BWD_BM = 128;   // rows of S (= rows of dX) per CTA
 constexpr int BWD_BJ = 128;   // columns of S per step
 constexpr int BWD_DCH = 384;  // columns of dX accumulated in TMEM per CTA
+// CTA-pair backward (loss_bwd_pair.cu, cta_group::2)
+constexpr int PAIR_BM = 128;   // rows of dX per CTA pair (64 per CTA)
+constexpr int PAIR_BJ = 256;   // columns of S per step
+constexpr int PAIR_DCH = 768;  // feature columns a pair accumulates (384 TMEM columns per CTA)
+constexpr int PAIR_SLOTS = 74; // CTA pairs resident at once on 148 SMs
 // CUDA-core fp32 tile geometry (loss_simt.cu)
 constexpr int SIMT_T = 64;    // forward tile (rows == cols)
 constexpr int SIMT_BR = 32;   // backward rows per block
@@ -94,5 +99,12 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
                      int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
                      const float* gscale, float weight, int accumulate, int jsplit, int fmt_bf16, float* dxh,
                      cudaStream_t s);
+
+// CTA-pair variant (loss_bwd_pair.cu): whole feature dimension per pair, S computed once per sweep; dpad <= 768
+bool pair_backward_supported(int64_t dpad);
+int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
+                          int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
+                          const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
+                          int fmt_bf16, float* dxh, cudaStream_t s);
 
 }  // namespace clibd
