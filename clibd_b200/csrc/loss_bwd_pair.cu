@@ -37,6 +37,7 @@ constexpr int P_STAGES = 3;
 constexpr int P_MAX_KB = PAIR_DCH / P_BK;         // 12
 constexpr int P_THREADS = 256;
 constexpr uint32_t P_TMEM_S_COL = 384;
+constexpr int P_PF_DIST = 2;                      // L2 prefetch distance in column tiles
 
 constexpr int P_SMEM_X = 0;                                         // resident Xhat rows: 96 KB
 constexpr int P_SMEM_G = P_SMEM_X + P_MAX_KB * P_XKB_BYTES;         // G~: 4 K blocks x 8 KB
@@ -49,6 +50,7 @@ constexpr int P_SMEM_TOTAL = P_SMEM_TMEMPTR + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL + 1024;
 static_assert(P_SMEM_ALLOC <= 232448, "pair backward kernel shared memory exceeds 227 KB");
 
+template <bool ST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                      const __grid_constant__ CUtensorMap tm_yt, int64_t N, int64_t ld, int64_t dvalid, int64_t row0,
@@ -83,7 +85,6 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int64_t jt0 = split * tiles_per_split;
     const int64_t jt1 = (jt0 + tiles_per_split < num_jt) ? (jt0 + tiles_per_split) : num_jt;
     const int half_w = piece_w >> 1;                                  // accumulator columns per piece per CTA
-    const uint32_t gsub_bytes = static_cast<uint32_t>(half_w) * 128;  // YhatT sub-tile of this CTA
     const int num_sst = (num_kb + 1) / 2;                             // S stages per column tile
     const int units = (PAIR_BJ / P_BK) * npieces;                     // (K block of the tile, piece) pairs
     const int num_gst = (units + 1) / 2;                              // gradient stages per column tile
@@ -115,11 +116,26 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t smem_base = smem_u32(smem);
 
     if (jt0 < jt1) {
+        // In the ST (static) instantiation d = 768: 12 K blocks, 3 gradient pieces of 256 columns.  A column tile
+        // is then 6 S stages + 6 gradient stages = 4 full turns of the 3-stage ring, so the ring slot and the
+        // mbarrier parity of every stage are compile-time constants and the loops below unroll into straight-line
+        // code (the generic loops cost ~530 issue cycles per 512-cycle stage: the tensor pipe starved on the issuer).
+        const int nkb = ST ? 12 : num_kb;
+        const int npc = ST ? 3 : npieces;
+        const int pw = ST ? 256 : piece_w;
+        const int hw = pw >> 1;
+        const int n_sst = ST ? 6 : num_sst;
+        const int n_gst = ST ? 6 : num_gst;
+        const int n_units = ST ? 12 : units;
         if (warp == 0) {  // ---------------- TMA producer (both CTAs; one elected lane issues)
             int stage = 0;
             uint32_t phase = 0;
             const int32_t xrow = static_cast<int32_t>(row0 + mt * PAIR_BM + rank * 64);
             const uint32_t xfull_l = mapa_u32(smem_u32(xfull), 0);
+            uint32_t full_l[P_STAGES];
+#pragma unroll
+            for (int i = 0; i < P_STAGES; ++i) full_l[i] = mapa_u32(smem_u32(&full[i]), 0);
+            const int32_t ytrow = static_cast<int32_t>(rank * hw);
             auto advance = [&]() {
                 if (++stage == P_STAGES) {
                     stage = 0;
@@ -127,25 +143,44 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 }
             };
             if (elect_one()) {
-                if (leader) mbar_arrive_expect_tx(xfull, 2u * num_kb * P_XKB_BYTES);
-                for (int kb = 0; kb < num_kb; ++kb)
+                if (leader) mbar_arrive_expect_tx(xfull, 2u * nkb * P_XKB_BYTES);
+                for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d_cg2(&tm_x, xfull_l, xres + kb * P_XKB_BYTES, kb * P_BK, xrow, kEvictNormal);
+            }
+            // all CTA pairs of a wave sweep the same columns in lockstep, so nobody warms L2 for anybody else:
+            // every CTA pulls its own future boxes into L2 P_PF_DIST tiles ahead (DRAM latency would otherwise
+            // be exposed on every ring refill; the ring itself only covers an L2 hit).
+            if (elect_one()) {
+                for (int64_t t = jt0; t < jt1 && t < jt0 + P_PF_DIST; ++t) {
+                    for (int kb = 0; kb < nkb; ++kb)
+                        tma_prefetch_2d(&tm_y, kb * P_BK, static_cast<int32_t>(t * PAIR_BJ + rank * 128));
+                    for (int kb2 = 0; kb2 < PAIR_BJ / P_BK; ++kb2)
+                        for (int pc = 0; pc < npc; ++pc)
+                            tma_prefetch_2d(&tm_yt, static_cast<int32_t>(t * PAIR_BJ + kb2 * P_BK), pc * pw + ytrow);
+                }
             }
             __syncwarp();
             auto load_grad = [&](int64_t t) {
-                for (int gs = 0; gs < num_gst; ++gs) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                const int32_t jcol = static_cast<int32_t>(t * PAIR_BJ);
+                const bool pf = t + P_PF_DIST < jt1;
+#pragma unroll
+                for (int gs = 0; gs < n_gst; ++gs) {
+                    const int st = ST ? (gs % P_STAGES) : stage;
+                    const uint32_t ph = ST ? static_cast<uint32_t>((gs / P_STAGES) & 1) : phase;
+                    mbar_wait(&empty[st], ph ^ 1);
                     if (elect_one()) {
-                        uint8_t* sb = ring + stage * P_STAGE_BYTES;
-                        const int nu = (units - 2 * gs) < 2 ? (units - 2 * gs) : 2;
-                        const uint32_t full_l = mapa_u32(smem_u32(&full[stage]), 0);
-                        if (leader) mbar_arrive_expect_tx(&full[stage], 2u * nu * gsub_bytes);
-                        for (int uu = 0; uu < nu; ++uu) {
-                            const int u = 2 * gs + uu;
-                            const int kb2 = u / npieces, pc = u - kb2 * npieces;
-                            tma_load_2d_cg2(&tm_yt, full_l, sb + uu * P_SUB_BYTES,
-                                            static_cast<int32_t>(t * PAIR_BJ + kb2 * P_BK),
-                                            static_cast<int32_t>(pc * piece_w + rank * half_w), kEvictNormal);
+                        uint8_t* sb = ring + st * P_STAGE_BYTES;
+                        const int nu = (n_units - 2 * gs) < 2 ? (n_units - 2 * gs) : 2;
+                        if (leader) mbar_arrive_expect_tx(&full[st], 2u * nu * hw * 128);
+#pragma unroll
+                        for (int uu = 0; uu < 2; ++uu) {
+                            if (uu < nu) {
+                                const int u = 2 * gs + uu;
+                                const int kb2 = u / npc, pc = u - kb2 * npc;
+                                tma_load_2d_cg2(&tm_yt, full_l[st], sb + uu * P_SUB_BYTES, jcol + kb2 * P_BK,
+                                                pc * pw + ytrow, kEvictNormal);
+                                if (pf) tma_prefetch_2d(&tm_yt, jcol + P_PF_DIST * PAIR_BJ + kb2 * P_BK, pc * pw + ytrow);
+                            }
                         }
                     }
                     __syncwarp();
@@ -154,16 +189,24 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             };
             for (int64_t t = jt0; t < jt1; ++t) {
                 const int32_t yrow = static_cast<int32_t>(t * PAIR_BJ + rank * 128);
-                for (int ss = 0; ss < num_sst; ++ss) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                const bool pf = t + P_PF_DIST < jt1;
+#pragma unroll
+                for (int ss = 0; ss < n_sst; ++ss) {
+                    const int st = ST ? (ss % P_STAGES) : stage;
+                    const uint32_t ph = ST ? static_cast<uint32_t>((ss / P_STAGES) & 1) : phase;
+                    mbar_wait(&empty[st], ph ^ 1);
                     if (elect_one()) {
-                        uint8_t* sb = ring + stage * P_STAGE_BYTES;
-                        const int nkk = (num_kb - 2 * ss) < 2 ? (num_kb - 2 * ss) : 2;
-                        const uint32_t full_l = mapa_u32(smem_u32(&full[stage]), 0);
-                        if (leader) mbar_arrive_expect_tx(&full[stage], 2u * nkk * P_SUB_BYTES);
-                        for (int kk = 0; kk < nkk; ++kk)
-                            tma_load_2d_cg2(&tm_y, full_l, sb + kk * P_SUB_BYTES, (2 * ss + kk) * P_BK, yrow,
-                                            kEvictNormal);
+                        uint8_t* sb = ring + st * P_STAGE_BYTES;
+                        const int nkk = (nkb - 2 * ss) < 2 ? (nkb - 2 * ss) : 2;
+                        if (leader) mbar_arrive_expect_tx(&full[st], 2u * nkk * P_SUB_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            if (kk < nkk) {
+                                tma_load_2d_cg2(&tm_y, full_l[st], sb + kk * P_SUB_BYTES, (2 * ss + kk) * P_BK, yrow,
+                                                kEvictNormal);
+                                if (pf) tma_prefetch_2d(&tm_y, (2 * ss + kk) * P_BK, yrow + P_PF_DIST * PAIR_BJ);
+                            }
+                        }
                     }
                     __syncwarp();
                     advance();
@@ -175,9 +218,11 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t s_tmem = tmem_base + P_TMEM_S_COL;
-            const uint32_t xaddr = smem_u32(xres);
-            const uint32_t gaddr = smem_u32(gbuf);
-            const uint32_t raddr = smem_u32(ring);
+            // descriptors of offset 0 of every operand region; tiles inside a region are reached by adding
+            // (byte offset >> 4) to the low word (all regions lie below 256 KB, no carry into other fields)
+            const uint64_t dx0 = make_sw128_kmajor_desc(smem_u32(xres));
+            const uint64_t dg0 = make_sw128_kmajor_desc(smem_u32(gbuf));
+            const uint64_t dr0 = make_sw128_kmajor_desc(smem_u32(ring));
             auto advance = [&]() {
                 if (++stage == P_STAGES) {
                     stage = 0;
@@ -185,26 +230,32 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 }
             };
             auto issue_grad = [&](int64_t tl) {  // tl = t - jt0 of the G~ tile to consume
-                mbar_wait_cluster(g_full, tl & 1);
+                mbar_wait(g_full, tl & 1);
                 tc_fence_after();
-                for (int gs = 0; gs < num_gst; ++gs) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sb = raddr + stage * P_STAGE_BYTES;
-                    const int nu = (units - 2 * gs) < 2 ? (units - 2 * gs) : 2;
-                    if (elect_one()) {
-                        for (int uu = 0; uu < nu; ++uu) {
-                            const int u = 2 * gs + uu;
-                            const int kb2 = u / npieces, pc = u - kb2 * npieces;
-                            const uint64_t da = make_sw128_kmajor_desc(gaddr + kb2 * P_XKB_BYTES);
-                            const uint64_t db = make_sw128_kmajor_desc(sb + uu * P_SUB_BYTES);
+                const uint32_t acc_first = tl > 0 ? 1u : 0u;
 #pragma unroll
-                            for (int k = 0; k < P_BK / 16; ++k)
-                                umma_f16_cg2(tmem_base + pc * half_w, desc_advance(da, k * 32), desc_advance(db, k * 32),
-                                             idesc_g, (tl > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
+                for (int gs = 0; gs < n_gst; ++gs) {
+                    const int st = ST ? (gs % P_STAGES) : stage;
+                    const uint32_t ph = ST ? static_cast<uint32_t>((gs / P_STAGES) & 1) : phase;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const int nu = (n_units - 2 * gs) < 2 ? (n_units - 2 * gs) : 2;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int uu = 0; uu < 2; ++uu) {
+                            if (uu < nu) {
+                                const int u = 2 * gs + uu;
+                                const int kb2 = u / npc, pc = u - kb2 * npc;
+                                const uint64_t da = dg0 + ((kb2 * P_XKB_BYTES) >> 4);
+                                const uint64_t db = dr0 + ((st * P_STAGE_BYTES + uu * P_SUB_BYTES) >> 4);
+#pragma unroll
+                                for (int k = 0; k < P_BK / 16; ++k)
+                                    umma_f16_cg2(tmem_base + pc * hw, da + 2 * k, db + 2 * k, idesc_g,
+                                                 (kb2 > 0 || k > 0) ? 1u : acc_first);
+                            }
                         }
-                        umma_commit_cg2(&empty[stage], 3);
-                        if (gs == num_gst - 1) umma_commit_cg2(g_empty, 3);
+                        umma_commit_cg2(&empty[st], 3);
+                        if (gs == n_gst - 1) umma_commit_cg2(g_empty, 3);
                     }
                     __syncwarp();
                     advance();
@@ -214,24 +265,28 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tc_fence_after();
             for (int64_t t = jt0; t < jt1; ++t) {
                 const int64_t tl = t - jt0;
-                mbar_wait_cluster(st_empty, (tl & 1) ^ 1);
+                mbar_wait(st_empty, (tl & 1) ^ 1);
                 tc_fence_after();
-                for (int ss = 0; ss < num_sst; ++ss) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sb = raddr + stage * P_STAGE_BYTES;
-                    const int nkk = (num_kb - 2 * ss) < 2 ? (num_kb - 2 * ss) : 2;
-                    if (elect_one()) {
-                        for (int kk = 0; kk < nkk; ++kk) {
-                            const uint64_t da = make_sw128_kmajor_desc(xaddr + (2 * ss + kk) * P_XKB_BYTES);
-                            const uint64_t db = make_sw128_kmajor_desc(sb + kk * P_SUB_BYTES);
 #pragma unroll
-                            for (int k = 0; k < P_BK / 16; ++k)
-                                umma_f16_cg2(s_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s,
-                                             (ss | kk | k) ? 1u : 0u);
+                for (int ss = 0; ss < n_sst; ++ss) {
+                    const int st = ST ? (ss % P_STAGES) : stage;
+                    const uint32_t ph = ST ? static_cast<uint32_t>((ss / P_STAGES) & 1) : phase;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const int nkk = (nkb - 2 * ss) < 2 ? (nkb - 2 * ss) : 2;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            if (kk < nkk) {
+                                const uint64_t da = dx0 + (((2 * ss + kk) * P_XKB_BYTES) >> 4);
+                                const uint64_t db = dr0 + ((st * P_STAGE_BYTES + kk * P_SUB_BYTES) >> 4);
+#pragma unroll
+                                for (int k = 0; k < P_BK / 16; ++k)
+                                    umma_f16_cg2(s_tmem, da + 2 * k, db + 2 * k, idesc_s, (ss | kk | k) ? 1u : 0u);
+                            }
                         }
-                        umma_commit_cg2(&empty[stage], 3);
-                        if (ss == num_sst - 1) umma_commit_cg2(st_full, 3);
+                        umma_commit_cg2(&empty[st], 3);
+                        if (ss == n_sst - 1) umma_commit_cg2(st_full, 3);
                     }
                     __syncwarp();
                     advance();
@@ -325,6 +380,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             tc_fence_after();
             const float wgt = weight * gscale[1];
             float* out = dxh + (split * n + lrow) * ld;
+            const bool vec_ok = (ld & 3) == 0;  // rows of dxh are then 16-byte aligned
             for (int pc = 0; pc < npieces; ++pc) {
                 for (int c0 = 0; c0 < half_w; c0 += 32) {
                     uint32_t v[32];
@@ -332,12 +388,36 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     tmem_ld_wait();
                     if (lrow < n) {
                         const int colbase = pc * piece_w + h * half_w + c0;
+                        if (vec_ok && c0 + 32 <= half_w && colbase + 32 <= dvalid) {
+                            float4* o4 = reinterpret_cast<float4*>(out + colbase);
+                            float4 old[8];
+                            if (accumulate) {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const int col = colbase + k;
-                            if (c0 + k < half_w && col < dvalid) {
-                                const float val = wgt * __uint_as_float(v[k]);
-                                out[col] = accumulate ? out[col] + val : val;
+                                for (int i = 0; i < 8; ++i) old[i] = o4[i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4 r;
+                                r.x = wgt * __uint_as_float(v[4 * i]);
+                                r.y = wgt * __uint_as_float(v[4 * i + 1]);
+                                r.z = wgt * __uint_as_float(v[4 * i + 2]);
+                                r.w = wgt * __uint_as_float(v[4 * i + 3]);
+                                if (accumulate) {
+                                    r.x += old[i].x;
+                                    r.y += old[i].y;
+                                    r.z += old[i].z;
+                                    r.w += old[i].w;
+                                }
+                                o4[i] = r;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const int col = colbase + k;
+                                if (c0 + k < half_w && col < dvalid) {
+                                    const float val = wgt * __uint_as_float(v[k]);
+                                    out[col] = accumulate ? out[col] + val : val;
+                                }
                             }
                         }
                     }
@@ -375,7 +455,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     CLIBD_REQUIRE(dpad % P_BK == 0 && dpad <= PAIR_DCH, "pair backward needs a padded feature dim <= 768");
     static bool attr_set = false;
     if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
+        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
+        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
         attr_set = true;
     }
     // gradient pieces: npieces equal pieces of width piece_w <= 256, piece_w a multiple of 16 (8 rows of YhatT per
@@ -396,9 +477,10 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     const uint32_t idesc_g = make_idesc_f16(PAIR_BM, piece_w, fmt_bf16 ? 1u : 0u);
     dim3 grid(static_cast<unsigned>(2 * ceil_div(n, PAIR_BM)), 1, static_cast<unsigned>(jsplit));
     ProfScope prof(PROF_LOSS_BWD_TC, s);
-    loss_bwd_pair_kernel<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(
-        tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces, piece_w, tiles_per_split, scale,
-        idesc_s, idesc_g, fmt_bf16, rowcoef, colcoef, gscale, weight, accumulate, dxh);
+    auto kern = (dpad == PAIR_DCH && npieces == 3) ? loss_bwd_pair_kernel<true> : loss_bwd_pair_kernel<false>;
+    kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
+                                               piece_w, tiles_per_split, scale, idesc_s, idesc_g, fmt_bf16, rowcoef,
+                                               colcoef, gscale, weight, accumulate, dxh);
     CLIBD_KERNEL_CHECK();
     return 0;
 }
