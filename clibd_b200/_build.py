@@ -35,6 +35,16 @@ def _stale() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Development builds (e.g. -DCLIBD_BWD_TIMING) next to the product library: lib/libclibd_b200_<name>.so"""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, f"libclibd_b200_{name}.so")
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", out, *sources()]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH

@@ -63,9 +63,11 @@ def load():
         return _test_double
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("CLIBD_B200_REBUILD"):
-        path = _build.build()
+    path = os.environ.get("CLIBD_B200_LIB")  # development: an instrumented build of the same sources
+    if not path:
+        path = _build.LIB_PATH
+        if not os.path.exists(path) or os.environ.get("CLIBD_B200_REBUILD"):
+            path = _build.build()
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
