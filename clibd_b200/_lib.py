@@ -29,7 +29,7 @@ SIGNATURES = {
     "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P,
                                         _P, _P]),
     "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P, _P, _P]),
-    "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P]),
+    "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P, _P]),
     "clibd_knn_normalize": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_knn_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
     "clibd_knn_search": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P]),
@@ -73,7 +73,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.clibd_abi_version() != 1:
+    if lib.clibd_abi_version() != 2:
         raise RuntimeError("clibd_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -96,6 +96,15 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
     p.off_posrow = take(sizeof(float) * n);
     p.off_dots = take(sizeof(float) * 3 * n);
     p.off_red = take(sizeof(double) * 512);
+    const int64_t H = label_hash_slots(N);
+    p.off_hown = take(sizeof(int32_t) * H);
+    p.off_hmin = take(sizeof(int32_t) * H);
+    p.off_hcnt = take(sizeof(int32_t) * H);
+    p.off_skey = take(sizeof(int32_t) * N);
+    p.off_sidx = take(sizeof(int32_t) * N);
+    p.off_iota = take(sizeof(int32_t) * N);
+    p.sort_tmp_bytes = class_sort_temp_bytes(N);
+    p.off_sorttmp = take(p.sort_tmp_bytes);
     p.total = off;
     return p;
 }
@@ -197,14 +206,23 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
     int32_t* rep = at<int32_t>(scratch, plan.off_rep);
     float* cnt = at<float>(scratch, plan.off_cnt);
     float* gscale = at<float>(scratch, plan.off_gscale);
-    if ((rc = launch_label_stats(labels, N, rep, cnt, stream))) return rc;
+    LabelScratch ls;
+    ls.own = at<int32_t>(scratch, plan.off_hown);
+    ls.hmin = at<int32_t>(scratch, plan.off_hmin);
+    ls.hcnt = at<int32_t>(scratch, plan.off_hcnt);
+    ls.skey = at<int32_t>(scratch, plan.off_skey);
+    ls.sidx = at<int32_t>(scratch, plan.off_sidx);
+    ls.iota = at<int32_t>(scratch, plan.off_iota);
+    ls.sort_tmp = at<void>(scratch, plan.off_sorttmp);
+    ls.sort_tmp_bytes = plan.sort_tmp_bytes;
+    if ((rc = launch_label_stats(labels, N, rep, cnt, ls, stream))) return rc;
     if ((rc = launch_gscale(cnt, N, path, gscale, stream))) return rc;
     bool used[3] = {false, false, false};
     for (int p = 0; p < 3; ++p)
         if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
     for (int m = 0; m < 3; ++m) {
         if (!used[m]) continue;
-        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], rep, cnt, N, d, at<float>(scratch, plan.off_Q[m]), stream)))
+        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], ls.skey, ls.sidx, cnt, N, d, at<float>(scratch, plan.off_Q[m]), stream)))
             return rc;
         if (tc) {
             if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16,
@@ -254,7 +272,8 @@ int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale
 
 int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
                         int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
-                        void* scratch, int64_t scratch_bytes, float grad_feat_scale, void* const dx[3],
+                        void* scratch, int64_t scratch_bytes, float grad_feat_scale, const float* grad_feat_scale_dev,
+                        void* const dx[3],
                         double* dscale_partial, clibd_stream_t stream) {
     const LossPlan plan = make_loss_plan(N, n, d, path);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
@@ -327,6 +346,7 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
         a.n = n;
         a.scale = logit_scale;
         a.grad_scale = grad_feat_scale;
+        a.grad_scale_dev = grad_feat_scale_dev;
         a.dx = dx ? dx[m] : nullptr;
         a.dots = dots + n_mod_used * n;
         if ((rc = launch_normalize_bwd(a, stream))) return rc;

@@ -32,6 +32,9 @@ struct LossPlan {
     size_t off_xh[3] = {0, 0, 0}, off_xhT[3] = {0, 0, 0}, off_Q[3] = {0, 0, 0}, off_dxh[3] = {0, 0, 0};
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
+    // label hash table (own/min/count per slot), rows sorted by class (keys, indices), sort input and CUB scratch
+    size_t off_hown = 0, off_hmin = 0, off_hcnt = 0, off_skey = 0, off_sidx = 0, off_iota = 0, off_sorttmp = 0;
+    size_t sort_tmp_bytes = 0;
     size_t total = 0;
 };
 
@@ -44,13 +47,22 @@ inline T* at(void* base, size_t off) {
 
 // ---- support kernels (loss_support.cu); all return 0 / error code ------------------
 int launch_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* inv_norm, cudaStream_t s);
-// rep[i] = lowest index with the same label, cnt[i] = number of rows sharing label i
-int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cnt, cudaStream_t s);
+// rep[i] = lowest index with the same label, cnt[i] = number of rows sharing label i; also the rows sorted by
+// (rep, index): ls.skey / ls.sidx
+struct LabelScratch {
+    int32_t *own, *hmin, *hcnt, *skey, *sidx, *iota;
+    void* sort_tmp;
+    size_t sort_tmp_bytes;
+};
+int64_t label_hash_slots(int64_t N);
+size_t class_sort_temp_bytes(int64_t N);
+int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cnt, const LabelScratch& ls,
+                       cudaStream_t s);
 // gscale[0] = power-of-two scale applied to 16-bit G operands (1 for bf16), gscale[1] = 1/gscale[0]
 int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStream_t s);
 // Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r
-int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* rep, const float* cnt,
-                      int64_t N, int64_t d, float* Q, cudaStream_t s);
+int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
+                      const float* cnt, int64_t N, int64_t d, float* Q, cudaStream_t s);
 // 16-bit normalised operand copies: xh [N,dpad] and its transpose xhT [dpad,npad] (zero padded)
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
                          int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s);
@@ -78,6 +90,7 @@ struct NormBwdArgs {
     float wp[2];            // their pair weights
     int64_t N, d, row0, n;
     float scale, grad_scale;
+    const float* grad_scale_dev;  // optional device scalar multiplied into grad_scale (may be null)
     void* dx;               // [n,d] in dtype, may be null
     float* dots;            // [n]
 };

@@ -6,6 +6,9 @@
 // Reference semantics: bioscanclip/model/loss_func.py:19-22 (label matrix), :55-56 / :186-187
 // (F.normalize), :65-69 / :195-200 (soft-target CE and the mean over the pair list).
 #include <climits>
+#include <string>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 #include "loss_plan.h"
@@ -31,39 +34,121 @@ __global__ void row_inv_norm_kernel(const T* __restrict__ x, int64_t n, int64_t 
     if (lane == 0) inv[row] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
 }
 
-__global__ void label_stats_kernel(const int64_t* __restrict__ labels, int64_t N, int32_t* __restrict__ rep,
-                                   float* __restrict__ cnt) {
-    __shared__ int s_cnt[kThreads / 32];
-    __shared__ int s_min[kThreads / 32];
-    const int64_t i = blockIdx.x;
-    const int64_t lab = labels[i];
-    int c = 0;
-    int mn = INT_MAX;
-    for (int64_t j = threadIdx.x; j < N; j += kThreads) {
-        if (labels[j] == lab) {
-            ++c;
-            mn = min(mn, static_cast<int>(j));
-        }
-    }
+// ---- 8-wide row access helpers (16-byte vectors when the row layout allows it) ---------------------
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
     }
-    if ((threadIdx.x & 31) == 0) {
-        s_cnt[threadIdx.x >> 5] = c;
-        s_min[threadIdx.x >> 5] = mn;
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tc = 0, tm = INT_MAX;
-        for (int w = 0; w < kThreads / 32; ++w) {
-            tc += s_cnt[w];
-            tm = min(tm, s_min[w]);
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <typename T>
+__host__ __device__ inline bool rows_vec8_ok(const void* base, int64_t d) {
+    return (d % 8 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+}
+
+// ---- label statistics: rep[i] = lowest index with the label of i, cnt[i] = class size --------------
+// (construct_label_metrix, loss_func.py:19-22, reduced to what the fused loss needs.)  Open-addressing hash
+// table keyed by label: a slot is claimed by storing the index of the first row that reaches it (the key is
+// then labels[owner], immutable), class minimum / count by atomicMin / atomicAdd -- both order-independent,
+// so the result is deterministic.  O(N) instead of the N x N comparison.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void hash_init_kernel(int32_t* __restrict__ own, int32_t* __restrict__ hmin, int32_t* __restrict__ hcnt,
+                                 int64_t H) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k < H) {
+        own[k] = -1;
+        hmin[k] = INT_MAX;
+        hcnt[k] = 0;
+    }
+}
+
+__global__ void hash_insert_kernel(const int64_t* __restrict__ labels, int64_t N, int64_t H, int32_t* own,
+                                   int32_t* hmin, int32_t* hcnt, int32_t* __restrict__ slot_of) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t lab = labels[i];
+    int64_t slot = static_cast<int64_t>(mix64(static_cast<uint64_t>(lab)) & static_cast<uint64_t>(H - 1));
+    while (true) {
+        int32_t o = *reinterpret_cast<volatile int32_t*>(own + slot);
+        if (o < 0) {
+            const int32_t prev = atomicCAS(own + slot, -1, static_cast<int32_t>(i));
+            o = prev < 0 ? static_cast<int32_t>(i) : prev;
         }
-        rep[i] = tm;
-        cnt[i] = static_cast<float>(tc);
+        if (labels[o] == lab) break;
+        slot = (slot + 1) & (H - 1);
     }
+    atomicMin(hmin + slot, static_cast<int32_t>(i));
+    atomicAdd(hcnt + slot, 1);
+    slot_of[i] = static_cast<int32_t>(slot);
+}
+
+__global__ void hash_lookup_kernel(int64_t N, const int32_t* __restrict__ hmin, const int32_t* __restrict__ hcnt,
+                                   int32_t* __restrict__ rep /* in: slot, out: representative */,
+                                   float* __restrict__ cnt, int32_t* __restrict__ iota) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t slot = rep[i];
+    rep[i] = hmin[slot];
+    cnt[i] = static_cast<float>(hcnt[slot]);
+    iota[i] = static_cast<int32_t>(i);
 }
 
 __global__ void gscale_kernel(const float* __restrict__ cnt, int64_t N, int path, float* __restrict__ gscale) {
@@ -86,81 +171,87 @@ __global__ void gscale_kernel(const float* __restrict__ cnt, int64_t N, int path
     }
 }
 
-// One block per row r.  Only representatives (rep[r] == r) do work: they add, in index
-// order, the normalised rows of their class.
-template <typename T>
+// Class sums over the rows sorted by (representative, index): one warp per class segment, members added in
+// index order (fixed summation order).  skey = sorted representatives, sidx = the rows in that order.
+template <typename T, bool VEC>
 __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restrict__ inv,
-                                  const int32_t* __restrict__ rep, const float* __restrict__ cnt, int64_t N,
-                                  int64_t d, float* __restrict__ Q) {
-    const int64_t r = blockIdx.x;
-    if (rep[r] != static_cast<int32_t>(r)) return;
-    float* qr = Q + r * d;
-    if (cnt[r] == 1.0f) {
-        const float iv = inv[r];
-        for (int64_t c = threadIdx.x; c < d; c += kThreads) qr[c] = load_as_float(x + r * d, c) * iv;
-        return;
-    }
-    __shared__ int s_list[kThreads];
-    __shared__ int s_woff[kThreads / 32 + 1];
-    constexpr int MAXQ = 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t cbase = 0; cbase < d; cbase += static_cast<int64_t>(kThreads) * MAXQ) {
-        float acc[MAXQ];
+                                  const int32_t* __restrict__ skey, const int32_t* __restrict__ sidx,
+                                  const float* __restrict__ cnt, int64_t N, int64_t d, float* __restrict__ Q) {
+    const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= N) return;
+    const int32_t r = skey[p];
+    if (p > 0 && skey[p - 1] == r) return;  // not the head of its segment
+    const int members = static_cast<int>(cnt[r]);
+    float* qr = Q + static_cast<int64_t>(r) * d;
+    if constexpr (VEC) {
+        for (int64_t c = lane * 8; c < d; c += 256) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int m = 0; m < members; ++m) {
+                const int64_t j = sidx[p + m];
+                const float iv = inv[j];
+                float v[8];
+                load8(x + j * d + c, v);
 #pragma unroll
-        for (int q = 0; q < MAXQ; ++q) acc[q] = 0.f;
-        for (int64_t j0 = r; j0 < N; j0 += kThreads) {  // members have index >= r
-            const int64_t j = j0 + threadIdx.x;
-            const bool flag = (j < N) && (rep[j] == static_cast<int32_t>(r));
-            const int total = __syncthreads_count(flag);
-            if (total == 0) continue;
-            const unsigned bal = __ballot_sync(0xffffffffu, flag);
-            if (lane == 0) s_woff[warp + 1] = __popc(bal);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_woff[0] = 0;
-                for (int w = 0; w < kThreads / 32; ++w) s_woff[w + 1] += s_woff[w];
+                for (int k = 0; k < 8; ++k) acc[k] += v[k] * iv;
             }
-            __syncthreads();
-            if (flag) s_list[s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = static_cast<int>(j);
-            __syncthreads();
-            for (int m = 0; m < total; ++m) {
-                const int64_t jj = s_list[m];
-                const float iv = inv[jj];
-#pragma unroll
-                for (int q = 0; q < MAXQ; ++q) {
-                    const int64_t c = cbase + threadIdx.x + static_cast<int64_t>(q) * kThreads;
-                    if (c < d) acc[q] += load_as_float(x + jj * d, c) * iv;
-                }
-            }
-            __syncthreads();
+            store8(qr + c, acc);
         }
-#pragma unroll
-        for (int q = 0; q < MAXQ; ++q) {
-            const int64_t c = cbase + threadIdx.x + static_cast<int64_t>(q) * kThreads;
-            if (c < d) qr[c] = acc[q];
+    } else {
+        for (int64_t c = lane; c < d; c += 32) {
+            float acc = 0.f;
+            for (int m = 0; m < members; ++m) {
+                const int64_t j = sidx[p + m];
+                acc += load_as_float(x + j * d, c) * inv[j];
+            }
+            qr[c] = acc;
         }
     }
 }
 
-// 32x32 tile: xh[row][col] = cvt(x*inv) (zero for col >= d), xhT[col][row] (zero for row >= N)
-template <typename T>
+// 64 x 64 tile: xh[row][col] = cvt(x * inv) (zero for col >= d), xhT[col][row] (zero for row >= N); 16-byte
+// global accesses on both outputs (and on the input when rows are 16-byte aligned)
+template <typename T, bool VEC>
 __global__ void make_operands_kernel(const T* __restrict__ x, const float* __restrict__ inv, int64_t N, int64_t d,
                                      int64_t dpad, int64_t npad, int fmt_bf16, uint16_t* __restrict__ xh,
                                      uint16_t* __restrict__ xhT) {
-    __shared__ uint16_t tile[32][33];
-    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32, r0 = static_cast<int64_t>(blockIdx.y) * 32;
-    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-        const int64_t row = r0 + dy, col = c0 + threadIdx.x;
-        uint16_t h = 0;
-        if (row < N && col < d) h = to_operand16(load_as_float(x + row * d, col) * (inv ? inv[row] : 1.f), fmt_bf16);
-        tile[dy][threadIdx.x] = h;
-        if (row < N && col < dpad) xh[row * dpad + col] = h;
+    __shared__ __align__(16) uint16_t tile[64][72];
+    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 64, r0 = static_cast<int64_t>(blockIdx.y) * 64;
+    for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) {
+        const int rr = idx >> 3, ch = idx & 7;
+        const int64_t row = r0 + rr, col = c0 + ch * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row < N) {
+            const float iv = inv ? inv[row] : 1.f;
+            if (VEC && col + 8 <= d) {
+                load8(x + row * d + col, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] *= iv;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (col + k < d) v[k] = load_as_float(x + row * d, col + k) * iv;
+            }
+        }
+        uint4 pk;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = pack2_operand16(v[2 * k], v[2 * k + 1], fmt_bf16);
+        *reinterpret_cast<uint4*>(&tile[rr][ch * 8]) = pk;
+        if (row < N && col < dpad) *reinterpret_cast<uint4*>(xh + row * dpad + col) = pk;
     }
     __syncthreads();
     if (xhT != nullptr) {
-        for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-            const int64_t col = c0 + dy, row = r0 + threadIdx.x;
-            if (col < dpad && row < npad) xhT[col * npad + row] = tile[threadIdx.x][dy];
+        for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) {
+            const int cc = idx >> 3, rch = idx & 7;
+            const int64_t col = c0 + cc, row = r0 + rch * 8;
+            if (col < dpad && row < npad) {
+                uint4 pk;
+                uint16_t* h = reinterpret_cast<uint16_t*>(&pk);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) h[k] = tile[rch * 8 + k][cc];
+                *reinterpret_cast<uint4*>(xhT + col * npad + row) = pk;
+            }
         }
     }
 }
@@ -260,42 +351,112 @@ __global__ void loss_finish_stage2_kernel(int64_t N, float scale, float w0, floa
     }
 }
 
-template <typename T>
+// One warp per local row: dxhat = (scale/N) * (sum_splits dxh - 2 * sum_partners w_p Q_partner[rep]),
+// dots = xhat . dxhat, dx = grad_scale * (dxhat - xhat * dots) / ||x||.  Rows up to 1024 columns stay in
+// registers between the dot product and the projection (one pass over HBM).
+template <typename T, bool VEC>
 __global__ void normalize_bwd_kernel(NormBwdArgs a) {
-    __shared__ float s_buf[kThreads / 32];
-    __shared__ float s_dot;
-    const int64_t i = blockIdx.x;
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= a.n) return;
     const int64_t gi = a.row0 + i;
     const T* xr = reinterpret_cast<const T*>(a.x) + gi * a.d;
     const float iv = a.inv_norm[gi];
     const int64_t rp = a.rep[gi];
     const float k1 = a.scale / static_cast<float>(a.N);
-    auto dxhat = [&](int64_t c) -> float {
-        float g = 0.f;
-        for (int s = 0; s < a.jsplit; ++s) g += a.dxh[(static_cast<int64_t>(s) * a.n + i) * a.d + c];
-        float t = 0.f;
-        if (a.Qp[0]) t = fmaf(a.wp[0], a.Qp[0][rp * a.d + c], t);
-        if (a.Qp[1]) t = fmaf(a.wp[1], a.Qp[1][rp * a.d + c], t);
-        return k1 * (g - 2.f * t);
-    };
-    float part = 0.f;
-    for (int64_t c = threadIdx.x; c < a.d; c += kThreads) part = fmaf(load_as_float(xr, c) * iv, dxhat(c), part);
-    part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < kThreads / 32; ++w) t += s_buf[w];
-        s_dot = t;
-        a.dots[i] = t;
-    }
-    __syncthreads();
-    if (a.dx == nullptr) return;
-    const float dot = s_dot;
-    T* dxr = reinterpret_cast<T*>(a.dx) + i * a.d;
-    for (int64_t c = threadIdx.x; c < a.d; c += kThreads) {
-        const float xh = load_as_float(xr, c) * iv;
-        store_from_float(dxr, c, a.grad_scale * (dxhat(c) - xh * dot) * iv);
+    const float gsc = a.grad_scale * (a.grad_scale_dev ? a.grad_scale_dev[0] : 1.f);
+    T* dxr = a.dx ? reinterpret_cast<T*>(a.dx) + i * a.d : nullptr;
+    if constexpr (VEC) {
+        auto dxhat8 = [&](int64_t c, float (&g)[8]) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = 0.f;
+            for (int s = 0; s < a.jsplit; ++s) {
+                float t[8];
+                load8(a.dxh + (static_cast<int64_t>(s) * a.n + i) * a.d + c, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] += t[k];
+            }
+            float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int pz = 0; pz < 2; ++pz) {
+                if (a.Qp[pz]) {
+                    float t[8];
+                    load8(a.Qp[pz] + rp * a.d + c, t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) q[k] = fmaf(a.wp[pz], t[k], q[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = k1 * (g[k] - 2.f * q[k]);
+        };
+        if (a.d <= 1024) {
+            float xv[4][8], gv[4][8];
+            float part = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int64_t c = lane * 8 + it * 256;
+                if (c < a.d) {
+                    load8(xr + c, xv[it]);
+                    dxhat8(c, gv[it]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        xv[it][k] *= iv;
+                        part = fmaf(xv[it][k], gv[it][k], part);
+                    }
+                }
+            }
+            const float dot = warp_sum(part);
+            if (lane == 0) a.dots[i] = dot;
+            if (dxr == nullptr) return;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int64_t c = lane * 8 + it * 256;
+                if (c < a.d) {
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] = gsc * (gv[it][k] - xv[it][k] * dot) * iv;
+                    store8(dxr + c, o);
+                }
+            }
+        } else {
+            float part = 0.f;
+            for (int64_t c = lane * 8; c < a.d; c += 256) {
+                float xv[8], gv[8];
+                load8(xr + c, xv);
+                dxhat8(c, gv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) part = fmaf(xv[k] * iv, gv[k], part);
+            }
+            const float dot = warp_sum(part);
+            if (lane == 0) a.dots[i] = dot;
+            if (dxr == nullptr) return;
+            for (int64_t c = lane * 8; c < a.d; c += 256) {
+                float xv[8], gv[8], o[8];
+                load8(xr + c, xv);
+                dxhat8(c, gv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = gsc * (gv[k] - xv[k] * iv * dot) * iv;
+                store8(dxr + c, o);
+            }
+        }
+    } else {
+        auto dxhat = [&](int64_t c) -> float {
+            float g = 0.f;
+            for (int s = 0; s < a.jsplit; ++s) g += a.dxh[(static_cast<int64_t>(s) * a.n + i) * a.d + c];
+            float t = 0.f;
+            if (a.Qp[0]) t = fmaf(a.wp[0], a.Qp[0][rp * a.d + c], t);
+            if (a.Qp[1]) t = fmaf(a.wp[1], a.Qp[1][rp * a.d + c], t);
+            return k1 * (g - 2.f * t);
+        };
+        float part = 0.f;
+        for (int64_t c = lane; c < a.d; c += 32) part = fmaf(load_as_float(xr, c) * iv, dxhat(c), part);
+        const float dot = warp_sum(part);
+        if (lane == 0) a.dots[i] = dot;
+        if (dxr == nullptr) return;
+        for (int64_t c = lane; c < a.d; c += 32) {
+            const float xh = load_as_float(xr, c) * iv;
+            store_from_float(dxr, c, gsc * (dxhat(c) - xh * dot) * iv);
+        }
     }
 }
 
@@ -317,10 +478,41 @@ int launch_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* i
     return 0;
 }
 
-int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cnt, cudaStream_t s) {
+int64_t label_hash_slots(int64_t N) {
+    int64_t H = 64;
+    while (H < 2 * N) H <<= 1;
+    return H;
+}
+
+size_t class_sort_temp_bytes(int64_t N) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
+                                    static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
+                                    static_cast<int>(N));
+    return bytes;
+}
+
+int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cnt, const LabelScratch& ls,
+                       cudaStream_t s) {
     if (N == 0) return 0;
-    label_stats_kernel<<<N, kThreads, 0, s>>>(labels, N, rep, cnt);
+    const int64_t H = label_hash_slots(N);
+    hash_init_kernel<<<ceil_div(H, kThreads), kThreads, 0, s>>>(ls.own, ls.hmin, ls.hcnt, H);
     CLIBD_KERNEL_CHECK();
+    hash_insert_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(labels, N, H, ls.own, ls.hmin, ls.hcnt, rep);
+    CLIBD_KERNEL_CHECK();
+    hash_lookup_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(N, ls.hmin, ls.hcnt, rep, cnt, ls.iota);
+    CLIBD_KERNEL_CHECK();
+    // rows grouped by class, in index order inside a class (stable LSD radix sort on the representative)
+    int end_bit = 1;
+    while ((int64_t(1) << end_bit) < N) ++end_bit;
+    size_t bytes = ls.sort_tmp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(ls.sort_tmp, bytes, rep, ls.skey, ls.iota, ls.sidx, static_cast<int>(N),
+                                                    0, end_bit, s);
+    if (e != cudaSuccess) {
+        set_error(std::string("class sort failed: ") + cudaGetErrorString(e));
+        return 2;
+    }
+    count_launch();
     return 0;
 }
 
@@ -330,10 +522,17 @@ int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStre
     return 0;
 }
 
-int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* rep, const float* cnt,
-                      int64_t N, int64_t d, float* Q, cudaStream_t s) {
+int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
+                      const float* cnt, int64_t N, int64_t d, float* Q, cudaStream_t s) {
     if (N == 0) return 0;
-    DISPATCH_DTYPE(dtype, (class_sums_kernel<T><<<N, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, rep, cnt, N, d, Q)));
+    const int64_t blocks = ceil_div(N * 32, kThreads);
+    const bool vec = rows_vec8_ok<void>(x, d) && rows_vec8_ok<void>(Q, d);
+    DISPATCH_DTYPE(dtype, {
+        if (vec && (sizeof(T) == 2 || d % 8 == 0))
+            class_sums_kernel<T, true><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, Q);
+        else
+            class_sums_kernel<T, false><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, Q);
+    });
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -341,11 +540,18 @@ int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
                          int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s) {
     const int64_t rows = npad > N ? npad : N;
-    dim3 grid(static_cast<unsigned>(ceil_div(dpad, 32)), static_cast<unsigned>(ceil_div(rows, 32)));
-    dim3 block(32, 8);
-    DISPATCH_DTYPE(dtype, (make_operands_kernel<T><<<grid, block, 0, s>>>(
-                              static_cast<const T*>(x), inv_norm, N, d, dpad, npad, fmt_bf16,
-                              static_cast<uint16_t*>(xh), static_cast<uint16_t*>(xhT))));
+    dim3 grid(static_cast<unsigned>(ceil_div(dpad, 64)), static_cast<unsigned>(ceil_div(rows, 64)));
+    const bool vec = rows_vec8_ok<void>(x, d);
+    DISPATCH_DTYPE(dtype, {
+        if (vec)
+            make_operands_kernel<T, true><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, N, d, dpad, npad,
+                                                                    fmt_bf16, static_cast<uint16_t*>(xh),
+                                                                    static_cast<uint16_t*>(xhT));
+        else
+            make_operands_kernel<T, false><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, N, d, dpad, npad,
+                                                                     fmt_bf16, static_cast<uint16_t*>(xh),
+                                                                     static_cast<uint16_t*>(xhT));
+    });
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -384,7 +590,16 @@ int launch_loss_finish(int64_t N, float scale, const float w[3], const float* cn
 
 int launch_normalize_bwd(const NormBwdArgs& a, cudaStream_t s) {
     if (a.n == 0) return 0;
-    DISPATCH_DTYPE(a.dtype, (normalize_bwd_kernel<T><<<a.n, kThreads, 0, s>>>(a)));
+    const int64_t blocks = ceil_div(a.n * 32, kThreads);
+    bool vec = rows_vec8_ok<void>(a.x, a.d) && rows_vec8_ok<void>(a.dxh, a.d) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
+    for (int p = 0; p < 2; ++p)
+        if (a.Qp[p]) vec = vec && rows_vec8_ok<void>(a.Qp[p], a.d);
+    DISPATCH_DTYPE(a.dtype, {
+        if (vec)
+            normalize_bwd_kernel<T, true><<<blocks, kThreads, 0, s>>>(a);
+        else
+            normalize_bwd_kernel<T, false><<<blocks, kThreads, 0, s>>>(a);
+    });
     CLIBD_KERNEL_CHECK();
     return 0;
 }

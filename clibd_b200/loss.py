@@ -176,17 +176,18 @@ class _FusedClipLossFn(torch.autograd.Function):
             ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in ctx.inv])
             outs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in dxs])
             w = _lib.float_array3(weights)
-            _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path,
-                                               ctx.scratch.data_ptr(), ctx.scratch.numel(), 1.0, outs,
-                                               dscale.data_ptr(), stream))
+            # grad_output stays on the device: the library multiplies it into the feature gradients
             gsum = grad_out
+            if world > 1 and sum_grads:  # backward of the differentiable all-gather: reduce-scatter(SUM) over ranks
+                gsum = grad_out.clone()
+                dist.all_reduce(gsum, group=group)
+            gsum = gsum.reshape(1).contiguous()
+            _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path,
+                                               ctx.scratch.data_ptr(), ctx.scratch.numel(), 1.0, gsum.data_ptr(), outs,
+                                               dscale.data_ptr(), stream))
             if world > 1:
-                if sum_grads:  # backward of the differentiable all-gather: reduce-scatter(SUM) over ranks
-                    gsum = grad_out.clone()
-                    dist.all_reduce(gsum, group=group)
                 dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
-            grads = [None if g is None else (g.float() * gsum).to(dtype) if dtype != torch.float32 else g * gsum
-                     for g in dxs]
+            grads = dxs
             gscale = None
             if ctx.has_scale and ctx.needs_input_grad[4]:
                 gscale = (dscale[0] * grad_out.double()).to(ctx.scale_dtype).reshape(())

@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 1
+#define CLIBD_ABI_VERSION 2
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -79,7 +79,8 @@ int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, floa
                               clibd_stream_t stream);
 
 /* Backward for the local rows.  dx[m]: [n_local, d] in `dtype` (NULL to skip) receives
- * grad_feat_scale * dL/dx; dscale_partial[0] receives sum over the local rows'
+ * grad_feat_scale * grad_feat_scale_dev[0] * dL/dx (the device scalar is optional, NULL = 1: it lets the
+ * caller pass autograd's grad_output without a host read); dscale_partial[0] receives sum over the local rows'
  * contribution to dL/d(logit_scale) for unit upstream gradient (all-reduce, then
  * multiply by the rank's own grad_output).  grad_feat_scale = sum over ranks of
  * grad_output (the reduce-scatter(SUM) convention of torch.distributed.nn.all_gather,
@@ -87,7 +88,8 @@ int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, floa
 int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
                         int64_t d, int64_t row0, int64_t n_local, float logit_scale,
                         const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
-                        float grad_feat_scale, void* const dx[3], double* dscale_partial, clibd_stream_t stream);
+                        float grad_feat_scale, const float* grad_feat_scale_dev, void* const dx[3],
+                        double* dscale_partial, clibd_stream_t stream);
 
 /* ---- cosine nearest-neighbour retrieval --------------------------------------------
  * Replaces make_prediction / find_closest_match's search (bioscanclip/util/util.py:

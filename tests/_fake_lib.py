@@ -87,8 +87,10 @@ class FakeLib:
         _arr(loss_out, (1,), np.float32)[0] = total / N
         return 0
 
-    def clibd_loss_backward(self, xs, dtype, ivs, N, d, row0, n, scale, w, path, scratch, nbytes, gscale, dxs,
+    def clibd_loss_backward(self, xs, dtype, ivs, N, d, row0, n, scale, w, path, scratch, nbytes, gscale, gscale_dev, dxs,
                             dscale, stream):
+        if gscale_dev:
+            gscale = gscale * float(_arr(gscale_dev, (1,), np.float32)[0])
         st = self.state[scratch]
         xh = self._inputs(xs, ivs, dtype, N, d)
         lab = st["labels"]

@@ -37,7 +37,7 @@ def stats(path, feats, labels, scale, weights):
     ds = torch.zeros(1, dtype=torch.float64, device=dev)
     outs = _lib.ptr_array3([t.data_ptr() for t in dxs] + [None] * (3 - len(feats)))
     _lib.check(lib.clibd_loss_backward(xs, _DT[feats[0].dtype], ivs, N, d, 0, N, scale, w, path, scratch.data_ptr(),
-                                       nbytes, 1.0, outs, ds.data_ptr(), stream))
+                                       nbytes, 1.0, None, outs, ds.data_ptr(), stream))
     torch.cuda.synchronize()
     return st[:3 * N].clone(), st[3 * N:].clone(), pos.clone(), float(loss), dxs, float(ds)
 
