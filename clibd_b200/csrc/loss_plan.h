@@ -113,6 +113,9 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
                      const float* gscale, float weight, int accumulate, int jsplit, int fmt_bf16, float* dxh,
                      cudaStream_t s);
 
+// CTA-pair forward (loss_fwd_pair.cu): 256 x 256 tiles, cta_group::2
+int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
+                        int fmt_bf16, float* rowpart, float* colpart, int num_sms, cudaStream_t s);
 // CTA-pair variant (loss_bwd_pair.cu): whole feature dimension per pair, S computed once per sweep; dpad <= 768
 bool pair_backward_supported(int64_t dpad);
 int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,

@@ -545,6 +545,8 @@ int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad,
                     int fmt_bf16, float* rowpart, float* colpart, cudaStream_t s) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % F_BK == 0, "padded feature dim must be a multiple of 64");
+    if (!std::getenv("CLIBD_FWD_SINGLE"))
+        return tc_forward_pair_cg2(xh_a, xh_b, N, dpad, row0, n, scale, fmt_bf16, rowpart, colpart, num_sms(), s);
     CUtensorMap tm_a, tm_b;
     int rc = make_tmap_2d_16bit(&tm_a, xh_a, N, dpad, dpad, F_BK, FWD_BM, fmt_bf16);
     if (rc) return rc;
