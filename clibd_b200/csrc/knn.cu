@@ -50,30 +50,39 @@ __global__ void knn_normalize_kernel(const T* __restrict__ x, int64_t n, int64_t
 // ------------------------------------------------------------------------------------------
 // tcgen05 screening kernel
 // ------------------------------------------------------------------------------------------
-constexpr int S_BM = 128, S_BN = 256, S_BK = 64, S_STAGES = 4;
-constexpr int S_A_BYTES = S_BM * S_BK * 2, S_B_BYTES = S_BN * S_BK * 2, S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
+// CTA pairs (cluster of 2, cta_group::2, M = 256): a pair screens 256 queries x 256 keys per tile; each CTA holds
+// its 128 query rows in TMEM (2 x 256 columns) and streams 128 query rows + 128 key rows per K block, so that the
+// shared-memory traffic (64 B/cycle operand reads + 64 B/cycle TMA writes) fits the 128 B/cycle the SM has --
+// the single-CTA 128 x 256 version needed 192 B/cycle and ran at ~70 % of the measured GEMM rate.
+constexpr int S_BM = 128, S_BN = 256, S_BK = 64, S_STAGES = 6;
+constexpr int S_QB = 2 * S_BM;  // queries per pair
+constexpr int S_A_BYTES = S_BM * S_BK * 2, S_B_BYTES = (S_BN / 2) * S_BK * 2, S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;
 constexpr int S_THREADS = 384, S_EPI_WARPS = 8;
 constexpr int S_SMEM_BARS = S_STAGES * S_STAGE_BYTES;
 constexpr int S_NUM_BARS = 2 * S_STAGES + 4;
 constexpr int S_SMEM_TMEMPTR = S_SMEM_BARS + S_NUM_BARS * 8;
-constexpr int S_SMEM_ALLOC = S_SMEM_TMEMPTR + 16 + 1024;
+constexpr int S_SMEM_ALLOC = S_SMEM_TMEMPTR + 16;
 
 template <int KP>
-__global__ void __launch_bounds__(S_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
 knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, int64_t Q,
                      int64_t K, int num_kb, int num_chunks, int64_t tiles_per_chunk, uint32_t idesc,
                      float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_SMEM_BARS);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + S_STAGES;
-    uint64_t* tfull_bar = bars + 2 * S_STAGES;
-    uint64_t* tempty_bar = bars + 2 * S_STAGES + 2;
+    uint64_t* full_bar = bars;                      // leader: both CTAs' operands landed
+    uint64_t* empty_bar = bars + S_STAGES;          // every CTA
+    uint64_t* tfull_bar = bars + 2 * S_STAGES;      // every CTA [2]
+    uint64_t* tempty_bar = bars + 2 * S_STAGES + 2; // leader [2]: 16 epilogue warps of the pair
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S_SMEM_TMEMPTR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t num_qb = (Q + S_BM - 1) / S_BM;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int64_t num_qb = (Q + S_QB - 1) / S_QB;
     const int64_t num_kt = (K + S_BN - 1) / S_BN;
     const int64_t num_units = num_qb * num_chunks;
 
@@ -86,79 +95,89 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], S_EPI_WARPS);
+            mbar_init(&tempty_bar[i], 2 * S_EPI_WARPS);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr, 512);
-        tmem_relinquish();
+        tmem_alloc_cg2(tmem_ptr, 512);
+        tmem_relinquish_cg2();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-                const int64_t qb = u % num_qb, kc = u / num_qb;
-                const int64_t kt0 = kc * tiles_per_chunk;
-                const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
-                for (int64_t kt = kt0; kt < kt1; ++kt) {
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+    if (warp == 0) {  // TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t full_l0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+        const bool elected = elect_one();
+        for (int64_t u = pair; u < num_units; u += num_pairs) {
+            const int64_t qb = u % num_qb, kc = u / num_qb;
+            const int64_t kt0 = kc * tiles_per_chunk;
+            const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
+            const int32_t qrow = static_cast<int32_t>(qb * S_QB + rank * S_BM);
+            for (int64_t kt = kt0; kt < kt1; ++kt) {
+                const int32_t krow = static_cast<int32_t>(kt * S_BN + rank * (S_BN / 2));
+#pragma unroll 1
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elected) {
                         uint8_t* sa = smem + stage * S_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], S_STAGE_BYTES);
-                        tma_load_2d(&tm_q, &full_bar[stage], sa, kb * S_BK, static_cast<int32_t>(qb * S_BM), kEvictNormal);
-                        tma_load_2d(&tm_k, &full_bar[stage], sa + S_A_BYTES, kb * S_BK, static_cast<int32_t>(kt * S_BN),
-                                    kEvictNormal);
-                        if (++stage == S_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * S_STAGE_BYTES);
+                        tma_load_2d_cg2(&tm_q, full_l0 + stage * 8, sa, kb * S_BK, qrow, kEvictNormal);
+                        tma_load_2d_cg2(&tm_k, full_l0 + stage * 8, sa + S_A_BYTES, kb * S_BK, krow, kEvictNormal);
+                    }
+                    __syncwarp();
+                    if (++stage == S_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, it = 0;
-            for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
-                const int64_t kc = u / num_qb;
-                const int64_t kt0 = kc * tiles_per_chunk;
-                const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
-                for (int64_t kt = kt0; kt < kt1; ++kt, ++it) {
-                    const uint32_t as = it & 1, aph = (it >> 1) & 1;
-                    mbar_wait(&tempty_bar[as], aph ^ 1);
+    } else if (warp == 1 && leader) {  // MMA issuer (leader CTA)
+        int stage = 0;
+        uint32_t phase = 0, it = 0;
+        const uint64_t d0 = make_sw128_kmajor_desc(smem_u32(smem));
+        const bool elected = elect_one();
+        for (int64_t u = pair; u < num_units; u += num_pairs) {
+            const int64_t kc = u / num_qb;
+            const int64_t kt0 = kc * tiles_per_chunk;
+            const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
+            for (int64_t kt = kt0; kt < kt1; ++kt, ++it) {
+                const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * S_BN;
+#pragma unroll 1
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * S_BN;
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * S_STAGE_BYTES);
-                        const uint64_t da = make_sw128_kmajor_desc(sa);
-                        const uint64_t db = make_sw128_kmajor_desc(sa + S_A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < S_BK / 16; ++k)
-                            umma_f16(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kb | k) ? 1u : 0u);
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
-                        if (++stage == S_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                    if (elected) {
+                        const uint64_t da = d0 + stage * (S_STAGE_BYTES >> 4);
+                        const uint64_t db = da + (S_A_BYTES >> 4);
+                        umma_f16_cg2(d_tmem, da, db, idesc, kb > 0 ? 1u : 0u);
+                        umma_f16_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
+                        umma_f16_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
+                        umma_f16_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+                        umma_commit_cg2(&empty_bar[stage], 3);
+                        if (kb == num_kb - 1) umma_commit_cg2(&tfull_bar[as], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == S_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
         }
     } else if (warp >= 4) {
         const int ew = warp - 4, q = warp & 3, h = ew >> 2;
+        const uint32_t tempty_l0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
         uint32_t it = 0;
-        for (int64_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+        for (int64_t u = pair; u < num_units; u += num_pairs) {
             const int64_t qb = u % num_qb, kc = u / num_qb;
             const int64_t kt0 = kc * tiles_per_chunk;
             const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
@@ -183,7 +202,7 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     if (c == 3) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                        if (lane == 0) mbar_arrive_cluster(tempty_l0 + as * 8);
                     }
                     const int32_t cb = static_cast<int32_t>(colbase) + c * 32;
                     float f[32];
@@ -225,7 +244,7 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                 }
             }
-            const int64_t row = qb * S_BM + q * 32 + lane;
+            const int64_t row = qb * S_QB + rank * S_BM + q * 32 + lane;
             if (row < Q) {
                 const int64_t base = (row * (2 * num_chunks) + (kc * 2 + h)) * KP;
 #pragma unroll
@@ -237,10 +256,10 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc_cg2(tmem_base, 512);
     }
 }
 
@@ -592,7 +611,7 @@ KnnPlan make_knn_plan(int64_t Q, int64_t K, int64_t d, int k, int path) {
     KnnPlan p;
     p.dpad = round_up(d, 64);
     p.kp = (k <= 5) ? 8 : 16;
-    const int64_t num_qb = ceil_div(Q, S_BM), num_kt = ceil_div(K, S_BN);
+    const int64_t num_qb = ceil_div(Q, S_QB), num_kt = ceil_div(K, S_BN);
     int64_t nc = ceil_div(2048, num_qb > 0 ? num_qb : 1);
     if (nc > 32) nc = 32;
     if (nc > num_kt) nc = num_kt;
@@ -713,10 +732,11 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
     if ((rc = launch_make_operands(keys32, DT_F32, nullptr, K, d, plan.dpad, 0, fmt_bf16, kh, nullptr, stream))) return rc;
     CUtensorMap tm_q, tm_k;
     if ((rc = make_tmap_2d_16bit(&tm_q, qh, Q, plan.dpad, plan.dpad, S_BK, S_BM, fmt_bf16))) return rc;
-    if ((rc = make_tmap_2d_16bit(&tm_k, kh, K, plan.dpad, plan.dpad, S_BK, S_BN, fmt_bf16))) return rc;
-    const int64_t units = ceil_div(Q, S_BM) * plan.num_chunks;
-    const int grid = static_cast<int>(units < sm_count() ? units : sm_count());
-    const uint32_t idesc = make_idesc_f16(S_BM, S_BN, fmt_bf16 ? 1u : 0u);
+    if ((rc = make_tmap_2d_16bit(&tm_k, kh, K, plan.dpad, plan.dpad, S_BK, S_BN / 2, fmt_bf16))) return rc;
+    const int64_t units = ceil_div(Q, S_QB) * plan.num_chunks;
+    const int64_t max_pairs = sm_count() / 2;
+    const int grid = 2 * static_cast<int>(units < max_pairs ? units : max_pairs);
+    const uint32_t idesc = make_idesc_f16(S_QB, S_BN, fmt_bf16 ? 1u : 0u);
     {
     ProfScope prof(PROF_KNN_SCREEN_TC, stream);
     if (plan.kp == 8) {
