@@ -276,39 +276,79 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     extern __shared__ uint8_t rr_smem[];
     const int C = num_lists * kp;
     double* sims = reinterpret_cast<double*>(rr_smem);                 // [C]
-    int32_t* ids = reinterpret_cast<int32_t*>(sims + C);               // [C]
-    float* qs = reinterpret_cast<float*>(ids + C);                     // [d]
+    int32_t* ids = reinterpret_cast<int32_t*>(sims + C);               // [C] survivors, compacted
+    float* scr = reinterpret_cast<float*>(ids + C);                    // [C] screened scores (selection scratch)
+    float* qs = scr + C;                                               // [d]
     __shared__ double s_best[2];
     __shared__ int s_besti[2];
     __shared__ int s_bestc[2];
+    __shared__ float s_thr;
+    __shared__ int s_ns;
     const int64_t qi = blockIdx.x;
     const int tid = threadIdx.x;
     const float* qrow = q32 + qi * d;
-    for (int c = tid; c < C; c += R_THREADS) ids[c] = cand_idx[qi * C + c];
+    for (int c = tid; c < C; c += R_THREADS) scr[c] = (cand_idx[qi * C + c] >= 0) ? cand_score[qi * C + c] : -INFINITY;
     for (int64_t t = tid; t < d; t += R_THREADS) qs[t] = qrow[t];
+    if (tid == 0) s_ns = 0;
     __syncthreads();
-    // one candidate per thread: float64 accumulation over d in index order (the oracle's order);
-    // a thread streams its own key row, 16 bytes at a time (lines stay in L1 between the 8 visits)
-    const bool vec4 = (d % 4 == 0);
+    // Prefilter: with s_k the k-th largest SCREENED score, at least k candidates have an exact score >= s_k - eps,
+    // so a candidate whose screened score is below s_k - 2 eps (exact < s_k - eps) cannot be in the exact top-k.
+    // Only the survivors are gathered and evaluated in float64 (typically ~k of the 2*chunks*KP candidates).
+    if (tid < 32) {
+        float kth_scr = -INFINITY;
+        for (int r = 0; r < k; ++r) {
+            float bs = -INFINITY;
+            int bc = -1;
+            for (int c = tid; c < C; c += 32) {
+                const float v = scr[c];
+                if (v > bs) {
+                    bs = v;
+                    bc = c;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (os > bs || (os == bs && oc >= 0 && (bc < 0 || oc < bc))) {
+                    bs = os;
+                    bc = oc;
+                }
+            }
+            kth_scr = bs;
+            if (bc < 0) break;  // fewer than k candidates: keep everything
+            if (tid == 0) scr[bc] = -INFINITY;
+            __syncwarp();
+        }
+        if (tid == 0) s_thr = (kth_scr == -INFINITY) ? -INFINITY : kth_scr - 2.0f * eps - 1e-6f;
+    }
+    __syncthreads();
+    const float thr = s_thr;
     for (int c = tid; c < C; c += R_THREADS) {
+        const int32_t id = cand_idx[qi * C + c];
+        if (id >= 0 && cand_score[qi * C + c] >= thr) ids[atomicAdd(&s_ns, 1)] = id;
+    }
+    __syncthreads();
+    const int ns = s_ns;
+    // one survivor per thread: float64 accumulation over d in index order (the oracle's order)
+    const bool vec4 = (d % 4 == 0);
+    for (int c = tid; c < ns; c += R_THREADS) {
         const int myid = ids[c];
         double acc = 0.0;
-        if (myid >= 0) {
-            const float* kr = k32 + static_cast<int64_t>(myid) * d;
-            if (vec4) {
-                const float4* kr4 = reinterpret_cast<const float4*>(kr);
-                for (int64_t t = 0; t < d / 4; ++t) {
-                    const float4 kv = __ldg(kr4 + t);
-                    acc += static_cast<double>(qs[4 * t]) * static_cast<double>(kv.x);
-                    acc += static_cast<double>(qs[4 * t + 1]) * static_cast<double>(kv.y);
-                    acc += static_cast<double>(qs[4 * t + 2]) * static_cast<double>(kv.z);
-                    acc += static_cast<double>(qs[4 * t + 3]) * static_cast<double>(kv.w);
-                }
-            } else {
-                for (int64_t t = 0; t < d; ++t) acc += static_cast<double>(qs[t]) * static_cast<double>(__ldg(kr + t));
+        const float* kr = k32 + static_cast<int64_t>(myid) * d;
+        if (vec4) {
+            const float4* kr4 = reinterpret_cast<const float4*>(kr);
+            for (int64_t t = 0; t < d / 4; ++t) {
+                const float4 kv = __ldg(kr4 + t);
+                acc += static_cast<double>(qs[4 * t]) * static_cast<double>(kv.x);
+                acc += static_cast<double>(qs[4 * t + 1]) * static_cast<double>(kv.y);
+                acc += static_cast<double>(qs[4 * t + 2]) * static_cast<double>(kv.z);
+                acc += static_cast<double>(qs[4 * t + 3]) * static_cast<double>(kv.w);
             }
+        } else {
+            for (int64_t t = 0; t < d; ++t) acc += static_cast<double>(qs[t]) * static_cast<double>(__ldg(kr + t));
         }
-        sims[c] = (myid >= 0) ? acc : -DBL_MAX;
+        sims[c] = acc;
     }
     __syncthreads();
     // k rounds of arg-best by (-sim, index)
@@ -316,7 +356,7 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     for (int r = 0; r < k; ++r) {
         double bs = -DBL_MAX;
         int bi = INT_MAX, bc = -1;
-        for (int c = tid; c < C; c += R_THREADS) {
+        for (int c = tid; c < ns; c += R_THREADS) {
             const int id = ids[c];
             if (id < 0) continue;
             const double s = sims[c];
@@ -766,7 +806,7 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
                        static_cast<double>(d) * 2.384185791015625e-07;
     CLIBD_CHECK_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int32_t) * 4, stream));
     const int C = plan.num_lists * plan.kp;
-    const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t)) + sizeof(float) * d;
+    const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t) + sizeof(float)) + sizeof(float) * d;
     CLIBD_REQUIRE(rr_smem <= 48 * 1024, "too many candidate lists for the re-rank kernel");
     {
     ProfScope prof(PROF_KNN_RERANK, stream);
