@@ -1,0 +1,97 @@
+"""Multi-GPU parity check, one process per GPU (launched by tests/test_multigpu.py or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port P \
+        tools/multigpu_check.py
+
+Loss: ClipLoss(world_size=W) on row shards (NCCL all-gather / all-reduce) must return the same loss as the
+single-process ContrastiveLoss on the concatenated batch, and each rank's gradient must be W x its slice of the
+full-batch gradient (the reduce-scatter(SUM) convention of torch.distributed.nn.all_gather's backward,
+reference loss_func.py:97).  kNN: keys sharded contiguously, per-rank top-k all-gathered and merged by
+(-sim, index) must be bit-identical to the unsharded search.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import clibd_b200 as cb  # noqa: E402
+from clibd_b200 import retrieval as R  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (n, d, nmod, dtype, operands, tol) in [(192, 96, 3, torch.float32, None, 2e-5),
+                                               (512, 768, 3, torch.bfloat16, None, 6e-3),  # both sides round the gradient to bf16 (2^-9)
+                                               (333, 768, 2, torch.float16, None, 2e-3)]:
+        N = n * world
+        gen = torch.Generator().manual_seed(11)
+        full = [torch.randn(N, d, generator=gen).to(dtype).to(dev) for _ in range(nmod)] + [None] * (3 - nmod)
+        labels = torch.randint(0, max(1, N // 8), (N,), generator=gen).to(dev)
+        scale_full = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+        leaves_full = [None if f is None else f.clone().requires_grad_(True) for f in full]
+        loss_full = cb.ContrastiveLoss(None, 1 / 0.07, tensor_core_operands=operands)(
+            leaves_full[0], leaves_full[1], leaves_full[2], labels, scale_full)
+        loss_full.backward()
+        sl = slice(rank * n, (rank + 1) * n)
+        leaves = [None if f is None else f[sl].clone().requires_grad_(True) for f in full]
+        scale = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+        mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world,
+                          tensor_core_operands=operands)
+        loss = mod(leaves[0], leaves[1], leaves[2], labels[sl], scale)
+        (loss * 3.0).backward()
+        torch.cuda.synchronize()
+        e_loss = abs(float(loss) - float(loss_full)) / abs(float(loss_full))
+        errs = []
+        for lf, ll in zip(leaves_full, leaves):
+            if lf is None:
+                continue
+            ref = lf.grad[sl].float() * (3.0 * world)
+            errs.append(float((ll.grad.float() - ref).norm() / ref.norm()))
+        # d loss / d logit_scale is replicated: every rank holds the full-batch derivative times its grad_output
+        e_ds = abs(float(scale.grad) - 3.0 * float(scale_full.grad)) / abs(3.0 * float(scale_full.grad))
+        good = e_loss < 1e-5 and max(errs) < tol and e_ds < 1e-3
+        ok &= good
+        print(f"[rank {rank}] loss n={n} d={d} nmod={nmod} {dtype}: loss_err={e_loss:.2e} "
+              f"grad_err={max(errs):.2e} dscale_err={e_ds:.2e} {'OK' if good else 'FAIL'}", flush=True)
+
+    # ---- kNN: sharded keys + all-gather + merge == unsharded
+    Q, K, d, k = 700, 20011, 768, 5
+    gen = torch.Generator().manual_seed(5)
+    keys = torch.randn(K, d, generator=gen)
+    keys[9000:9500] = keys[100:600]  # exact duplicates straddling the shard boundaries
+    keys[K - 300:] = keys[200:500]
+    q = keys[torch.randint(0, K, (Q,), generator=gen)] + 0.05 * torch.randn(Q, d, generator=gen)
+    q32, k32 = R.normalize_rows(q.to(dev), dev), R.normalize_rows(keys.to(dev), dev)
+    s_all, i_all, _ = R.search_normalized(q32, k32, k, mode="fp16")
+    per = (K + world - 1) // world
+    lo, hi = min(K, rank * per), min(K, (rank + 1) * per)
+    s, i, _ = R.search_normalized(q32, k32[lo:hi].contiguous(), k, key_offset=lo, mode="fp16")
+    all_s = torch.empty((world,) + tuple(s.shape), dtype=torch.float64, device=dev)
+    all_i = torch.empty((world,) + tuple(i.shape), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_s, s)
+    dist.all_gather_into_tensor(all_i, i)
+    m64, _, mi = R.merge_topk(all_s, all_i)
+    good = bool(torch.equal(mi, i_all) and torch.equal(m64, s_all))
+    ok &= good
+    print(f"[rank {rank}] knn shard merge bit-exact: {'OK' if good else 'FAIL'}", flush=True)
+
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if int(flag) != 1:
+        sys.exit(1)
+    if rank == 0:
+        print("MULTIGPU_CHECK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
