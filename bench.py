@@ -263,20 +263,34 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" \
         if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
 
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    except Exception:  # noqa: BLE001
+        pass
+
+    def dram_traffic(key):
+        # ncu-measured DRAM bytes per launch; only valid for the configuration it was captured on
+        t = traffic.get(key)
+        if t and t.get("config") == f"N={N} d={d} n_gpus={world}":
+            return t["bytes_per_launch"]
+        return None
+
     def roof(slot, flops_per_launch, name):
         if prof_n[slot] == 0:
             return None
         avg_ms = prof_ms[slot] / prof_n[slot]
         ach = flops_per_launch / (avg_ms * 1e-3) / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "launches": int(prof_n[slot]),
+                "frac": ach / peak_tf, "traffic": dram_traffic(name), "avg_launch_ms": avg_ms,
+                "launches": int(prof_n[slot]),
                 "algorithmic_flops_per_launch": flops_per_launch, "peak_source": peak_src,
                 "share_of_step": prof_ms[slot] / (ms_total if ms_total > 0 else 1)}
 
     # algorithmic work: forward 2*n*N*d per unordered pair launch; backward 4*n*N*d per unordered
     # pair = 2*n*N*d per ordered-sweep launch (the S recompute is NOT credited)
-    roofline = roof(1, 2.0 * n * N * d, "loss_bwd_tc_kernel")
-    roofline_fwd = roof(0, 2.0 * n * N * d, "loss_fwd_tc_kernel")
+    roofline = roof(1, 2.0 * n * N * d, "loss_bwd_pair_kernel")
+    roofline_fwd = roof(0, 2.0 * n * N * d, "loss_fwd_pair_kernel")
     step_frac = (18.0 * n * N * d) / (ms_step * 1e-3) / 1e12 / peak_tf
 
     out = {
