@@ -11,6 +11,7 @@
 //                  rigorous rounding bound is below its k-th exact score; all other queries are
 //                  redone exhaustively in float64.
 //   exact path   : 64x64 float64 tiles on CUDA cores + per-row selection.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 
@@ -63,11 +64,25 @@ constexpr int S_NUM_BARS = 2 * S_STAGES + 4;
 constexpr int S_SMEM_TMEMPTR = S_SMEM_BARS + S_NUM_BARS * 8;
 constexpr int S_SMEM_ALLOC = S_SMEM_TMEMPTR + 16;
 
+__global__ void knn_fill_kernel(float* __restrict__ p, int64_t n, float v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// atomic max on a float that may be negative (never NaN here): signed-int order for >= 0, reversed unsigned order below
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 template <int KP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
 knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, int64_t Q,
-                     int64_t K, int num_kb, int num_chunks, int64_t tiles_per_chunk, uint32_t idesc,
-                     float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
+                     int64_t K, int num_kb, int num_chunks, int64_t tiles_per_chunk, uint32_t idesc, int k,
+                     float floor_delta, float* rowfloor, float* __restrict__ cand_score,
+                     int32_t* __restrict__ cand_idx) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -181,11 +196,17 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const int64_t qb = u % num_qb, kc = u / num_qb;
             const int64_t kt0 = kc * tiles_per_chunk;
             const int64_t kt1 = (kt0 + tiles_per_chunk < num_kt) ? kt0 + tiles_per_chunk : num_kt;
+            // Row floor: some earlier unit of this row found k keys with screened score >= T; their exact scores are
+            // >= T - eps, so a key screened below T - 2 eps (exact < T - eps) can neither enter nor tie the exact
+            // top-k.  Lists start filled with sentinels (index -1) at that floor: after the first chunk of a row
+            // almost no column passes the one-compare-per-32-columns test below.
+            const int64_t row = qb * S_QB + rank * S_BM + q * 32 + lane;
+            const float fl = (row < Q) ? *(volatile float*)(rowfloor + row) : -INFINITY;
             float ls[KP];
             int32_t li[KP];
 #pragma unroll
             for (int i = 0; i < KP; ++i) {
-                ls[i] = -INFINITY;
+                ls[i] = fl;
                 li[i] = -1;
             }
             for (int64_t kt = kt0; kt < kt1; ++kt, ++it) {
@@ -244,14 +265,20 @@ knn_screen_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                 }
             }
-            const int64_t row = qb * S_QB + rank * S_BM + q * 32 + lane;
             if (row < Q) {
                 const int64_t base = (row * (2 * num_chunks) + (kc * 2 + h)) * KP;
+                float kth = -INFINITY;
+                bool have_k = false;
 #pragma unroll
                 for (int i = 0; i < KP; ++i) {
                     cand_score[base + i] = ls[i];
                     cand_idx[base + i] = li[i];
+                    if (i == k - 1) {
+                        kth = ls[i];
+                        have_k = li[i] >= 0;
+                    }
                 }
+                if (have_k) atomic_max_float(rowfloor + row, kth - floor_delta);
             }
         }
     }
@@ -287,47 +314,67 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     const int64_t qi = blockIdx.x;
     const int tid = threadIdx.x;
     const float* qrow = q32 + qi * d;
-    for (int c = tid; c < C; c += R_THREADS) scr[c] = (cand_idx[qi * C + c] >= 0) ? cand_score[qi * C + c] : -INFINITY;
+    __shared__ int s_nc;
+    if (tid == 0) {
+        s_ns = 0;
+        s_nc = 0;
+    }
     for (int64_t t = tid; t < d; t += R_THREADS) qs[t] = qrow[t];
-    if (tid == 0) s_ns = 0;
     __syncthreads();
+    // compact the real candidates (most lists hold only floor sentinels, index -1); cidx aliases the tail of sims[]
+    // until the float64 evaluation starts (sims is only written after the survivors have been chosen)
+    int32_t* cidx = reinterpret_cast<int32_t*>(sims);
+    for (int c = tid; c < C; c += R_THREADS) {
+        const int32_t id = cand_idx[qi * C + c];
+        if (id >= 0) {
+            const int pos = atomicAdd(&s_nc, 1);
+            scr[pos] = cand_score[qi * C + c];
+            cidx[pos] = id;
+        }
+    }
+    __syncthreads();
+    const int nc = s_nc;
     // Prefilter: with s_k the k-th largest SCREENED score, at least k candidates have an exact score >= s_k - eps,
     // so a candidate whose screened score is below s_k - 2 eps (exact < s_k - eps) cannot be in the exact top-k.
-    // Only the survivors are gathered and evaluated in float64 (typically ~k of the 2*chunks*KP candidates).
+    // Only the survivors are gathered and evaluated in float64 (typically ~k of the candidates).
     if (tid < 32) {
         float kth_scr = -INFINITY;
+        float prev = INFINITY;
+        int prev_taken = 0;  // how many entries equal to `prev` have been counted already
         for (int r = 0; r < k; ++r) {
+            // r-th largest value with multiplicity, without modifying scr[]: largest value < prev, or prev again
+            // while copies of it remain
             float bs = -INFINITY;
-            int bc = -1;
-            for (int c = tid; c < C; c += 32) {
+            int cnt_prev = 0;
+            for (int c = tid; c < nc; c += 32) {
                 const float v = scr[c];
-                if (v > bs) {
-                    bs = v;
-                    bc = c;
-                }
+                if (v == prev) ++cnt_prev;
+                else if (v < prev && v > bs) bs = v;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-                if (os > bs || (os == bs && oc >= 0 && (bc < 0 || oc < bc))) {
-                    bs = os;
-                    bc = oc;
-                }
+                bs = fmaxf(bs, __shfl_xor_sync(0xffffffffu, bs, o));
+                cnt_prev += __shfl_xor_sync(0xffffffffu, cnt_prev, o);
             }
+            if (r > 0 && cnt_prev > prev_taken) {
+                ++prev_taken;
+                kth_scr = prev;
+                continue;
+            }
+            if (bs == -INFINITY) {  // fewer than k candidates: keep everything
+                kth_scr = -INFINITY;
+                break;
+            }
+            prev = bs;
+            prev_taken = 1;
             kth_scr = bs;
-            if (bc < 0) break;  // fewer than k candidates: keep everything
-            if (tid == 0) scr[bc] = -INFINITY;
-            __syncwarp();
         }
         if (tid == 0) s_thr = (kth_scr == -INFINITY) ? -INFINITY : kth_scr - 2.0f * eps - 1e-6f;
     }
     __syncthreads();
     const float thr = s_thr;
-    for (int c = tid; c < C; c += R_THREADS) {
-        const int32_t id = cand_idx[qi * C + c];
-        if (id >= 0 && cand_score[qi * C + c] >= thr) ids[atomicAdd(&s_ns, 1)] = id;
-    }
+    for (int c = tid; c < nc; c += R_THREADS)
+        if (scr[c] >= thr) ids[atomicAdd(&s_ns, 1)] = cidx[c];
     __syncthreads();
     const int ns = s_ns;
     // one survivor per thread: float64 accumulation over d in index order (the oracle's order)
@@ -405,18 +452,19 @@ knn_rerank_kernel(const float* __restrict__ q32, const float* __restrict__ k32, 
     }
     // completeness proof: every key outside the candidate set lies in some sub-range whose list is
     // full; its screened score is <= that list's last score t, hence its exact score <= t + eps.
-    if (tid == 0) {
-        bool ok = true;
-        for (int l = 0; l < num_lists; ++l) {
-            const float t = cand_score[(qi * num_lists + l) * kp + kp - 1];
-            const int32_t last = cand_idx[(qi * num_lists + l) * kp + kp - 1];
-            if (last < 0) continue;  // list not full: the whole sub-range is in the candidate set
-            if (!(static_cast<double>(t) + static_cast<double>(eps) < kth)) ok = false;
-        }
-        if (!ok) {
-            const int slot = atomicAdd(n_flagged, 1);
-            flagged[slot] = static_cast<int32_t>(qi);
-        }
+    int bad = 0;
+    for (int l = tid; l < num_lists; l += R_THREADS) {
+        const float t = cand_score[(qi * num_lists + l) * kp + kp - 1];
+        const int32_t last = cand_idx[(qi * num_lists + l) * kp + kp - 1];
+        // list not full: every key of the sub-range is either a candidate or was dropped below a row floor
+        // T - 2 eps - 1e-6 (T = k-th best screened score of some earlier list), i.e. strictly below kth
+        if (last < 0) continue;
+        if (!(static_cast<double>(t) + static_cast<double>(eps) < kth)) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (tid == 0 && bad) {
+        const int slot = atomicAdd(n_flagged, 1);
+        flagged[slot] = static_cast<int32_t>(qi);
     }
 }
 
@@ -642,7 +690,7 @@ struct KnnPlan {
     int kp = 8, num_chunks = 1, num_lists = 2;
     int64_t tiles_per_chunk = 0;
     int64_t exact_rows = 0;
-    size_t off_qh = 0, off_kh = 0, off_cs = 0, off_ci = 0, off_flag = 0, off_nflag = 0, off_buf = 0, total = 0;
+    size_t off_qh = 0, off_kh = 0, off_cs = 0, off_ci = 0, off_floor = 0, off_flag = 0, off_nflag = 0, off_buf = 0, total = 0;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -652,8 +700,14 @@ KnnPlan make_knn_plan(int64_t Q, int64_t K, int64_t d, int k, int path) {
     p.dpad = round_up(d, 64);
     p.kp = (k <= 5) ? 8 : 16;
     const int64_t num_qb = ceil_div(Q, S_QB), num_kt = ceil_div(K, S_BN);
+    // chunks of the key range: enough units to fill the machine when there are few queries, and -- because every
+    // query block sweeps a chunk while the CTA pairs drift apart -- small enough (<= 24 MB of 16-bit keys) that a
+    // chunk stays resident in L2 instead of being re-fetched from HBM by every pair
     int64_t nc = ceil_div(2048, num_qb > 0 ? num_qb : 1);
     if (nc > 32) nc = 32;
+    const int64_t l2_tiles = std::max<int64_t>(8, (int64_t(24) << 20) / (S_BN * p.dpad * 2));
+    const int64_t nc_l2 = std::min<int64_t>(64, ceil_div(num_kt, l2_tiles));
+    if (nc < nc_l2) nc = nc_l2;
     if (nc > num_kt) nc = num_kt;
     if (nc < 1) nc = 1;
     p.tiles_per_chunk = ceil_div(num_kt, nc);
@@ -675,6 +729,7 @@ KnnPlan make_knn_plan(int64_t Q, int64_t K, int64_t d, int k, int path) {
         p.off_kh = take(2 * static_cast<size_t>(K) * p.dpad);
         p.off_cs = take(sizeof(float) * Q * p.num_lists * p.kp);
         p.off_ci = take(sizeof(int32_t) * Q * p.num_lists * p.kp);
+        p.off_floor = take(sizeof(float) * Q);
     }
     p.off_flag = take(sizeof(int32_t) * Q);
     p.off_nflag = take(sizeof(int32_t) * 4);
@@ -777,6 +832,16 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
     const int64_t max_pairs = sm_count() / 2;
     const int grid = 2 * static_cast<int>(units < max_pairs ? units : max_pairs);
     const uint32_t idesc = make_idesc_f16(S_QB, S_BN, fmt_bf16 ? 1u : 0u);
+    // rigorous bound on |screened - exact| for unit-norm rows: operand rounding (2u + u^2) with
+    // u = 2^-11 (f16) or 2^-8 (bf16), f16 subnormal flush (<= 2 * sqrt(d) * 2^-25), and fp32
+    // accumulation of d exact products inside the tensor core (<= d * 2^-22).
+    const double u = fmt_bf16 ? 0.00390625 : 0.00048828125;
+    const double eps = (2.0 * u + u * u) * 1.0001 + 2.0 * sqrt(static_cast<double>(d)) * 2.98e-8 +
+                       static_cast<double>(d) * 2.384185791015625e-07;
+    const float floor_delta = 2.0f * static_cast<float>(eps) + 1e-6f;
+    float* rowfloor = at<float>(scratch, plan.off_floor);
+    knn_fill_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(rowfloor, Q, -INFINITY);
+    CLIBD_KERNEL_CHECK();
     {
     ProfScope prof(PROF_KNN_SCREEN_TC, stream);
     if (plan.kp == 8) {
@@ -786,7 +851,7 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
             attr8 = true;
         }
         knn_screen_tc_kernel<8><<<grid, S_THREADS, S_SMEM_ALLOC, stream>>>(tm_q, tm_k, Q, K, static_cast<int>(plan.dpad / S_BK),
-                                                                           plan.num_chunks, plan.tiles_per_chunk, idesc, cs, ci);
+                                                                           plan.num_chunks, plan.tiles_per_chunk, idesc, k, floor_delta, rowfloor, cs, ci);
     } else {
         static bool attr16 = false;
         if (!attr16) {
@@ -794,16 +859,10 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
             attr16 = true;
         }
         knn_screen_tc_kernel<16><<<grid, S_THREADS, S_SMEM_ALLOC, stream>>>(tm_q, tm_k, Q, K, static_cast<int>(plan.dpad / S_BK),
-                                                                            plan.num_chunks, plan.tiles_per_chunk, idesc, cs, ci);
+                                                                            plan.num_chunks, plan.tiles_per_chunk, idesc, k, floor_delta, rowfloor, cs, ci);
     }
     }
     CLIBD_KERNEL_CHECK();
-    // rigorous bound on |screened - exact| for unit-norm rows: operand rounding (2u + u^2) with
-    // u = 2^-11 (f16) or 2^-8 (bf16), f16 subnormal flush (<= 2 * sqrt(d) * 2^-25), and fp32
-    // accumulation of d exact products inside the tensor core (<= d * 2^-22).
-    const double u = fmt_bf16 ? 0.00390625 : 0.00048828125;
-    const double eps = (2.0 * u + u * u) * 1.0001 + 2.0 * sqrt(static_cast<double>(d)) * 2.98e-8 +
-                       static_cast<double>(d) * 2.384185791015625e-07;
     CLIBD_CHECK_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int32_t) * 4, stream));
     const int C = plan.num_lists * plan.kp;
     const size_t rr_smem = static_cast<size_t>(C) * (sizeof(double) + sizeof(int32_t) + sizeof(float)) + sizeof(float) * d;
