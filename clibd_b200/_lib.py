@@ -35,6 +35,10 @@ SIGNATURES = {
     "clibd_knn_search": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P]),
     "clibd_knn_merge": (_INT, [_P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
     "clibd_topk_accuracy": (_INT, [_P, _I64, _INT, _P, _I64, _P, _P, _INT, _c.c_int32, _P, _P, _P, _P]),
+    "clibd_embed_append": (_INT, [_P, _INT, _I64, _I64, _P, _I64, _I64, _I64, _P]),
+    "clibd_softmax_mean_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
+    "clibd_softmax_mean_forward": (_INT, [_P, _INT, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "clibd_softmax_mean_backward": (_INT, [_P, _P, _INT, _I64, _I64, _I64, _P, _P]),
 }
 
 _lib = None
@@ -73,7 +77,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.clibd_abi_version() != 2:
+    if lib.clibd_abi_version() != 3:
         raise RuntimeError("clibd_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 2
+#define CLIBD_ABI_VERSION 3
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -127,6 +127,26 @@ int clibd_knn_merge(const double* sims64, const int64_t* idx, int parts, int64_t
 int clibd_topk_accuracy(const int64_t* idx, int64_t n_query, int kmax, const int32_t* key_ids, int64_t n_key,
                         const int32_t* query_ids, const int32_t* k_list /* host */, int nk, int32_t max_class,
                         int64_t* micro_hits, int32_t* class_hit, int32_t* class_cnt, clibd_stream_t stream);
+
+/* ---- seams next to the hot path (SURVEY.md section 8 f, ranks 2 and 3) ----------------------------
+ * Embedding hand-off: replaces `F.normalize(output, dim=-1).cpu().tolist()` per batch followed by
+ * `np.array(list)` (bioscanclip/epoch/inference_epoch.py:96-101, 108-119).  Rows of x [n, d] (dtype 0/1/2)
+ * are L2-normalised (x / max(||x||_2, 1e-12), float32 arithmetic) and written as float32 into rows
+ * [row_offset, row_offset + n) of the caller's device store [store_rows, store_ld] (store_ld >= d). */
+int clibd_embed_append(const void* x, int dtype, int64_t n, int64_t d, float* store, int64_t store_rows,
+                       int64_t store_ld, int64_t row_offset, clibd_stream_t stream);
+
+/* BarcodeBERT head: out[b, c] = mean_t softmax_c(logits[b, t, :])  (`logits.softmax(dim=-1).mean(dim=1)`,
+ * bioscanclip/model/dna_encoder.py:137) and its backward
+ *   grad_logits[b,t,c] = p[b,t,c] / T * (grad_out[b,c] - sum_c' grad_out[b,c'] p[b,t,c']).
+ * logits / grad_logits: [n, tokens, classes] contiguous in `dtype`; out / grad_out: [n, classes] in `dtype`.
+ * The probabilities are recomputed in the backward; no [n, tokens, classes] intermediate is stored.
+ * scratch: clibd_softmax_mean_scratch_bytes() bytes (0 for rows of <= 1024 16-byte-aligned values). */
+int64_t clibd_softmax_mean_scratch_bytes(int64_t n, int64_t tokens, int64_t classes, int dtype);
+int clibd_softmax_mean_forward(const void* logits, int dtype, int64_t n, int64_t tokens, int64_t classes, void* out,
+                               void* scratch, int64_t scratch_bytes, clibd_stream_t stream);
+int clibd_softmax_mean_backward(const void* logits, const void* grad_out, int dtype, int64_t n, int64_t tokens,
+                                int64_t classes, void* grad_logits, clibd_stream_t stream);
 
 #ifdef __cplusplus
 }

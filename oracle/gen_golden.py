@@ -239,6 +239,65 @@ def gen_accuracy():
     print("wrote", path)
 
 
+def load_ref_function(path, func_name, class_name=None, extra_ns=None):
+    """Extract one function (or method) from a reference source file with ast and compile it unmodified."""
+    tree = ast.parse(open(path).read())
+    nodes = tree.body
+    if class_name is not None:
+        cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+        nodes = cls.body
+    fn = next(n for n in nodes if isinstance(n, ast.FunctionDef) and n.name == func_name)
+    ns = dict(extra_ns or {})
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), os.path.basename(path) + ":" + func_name, "exec"), ns)
+    return ns[func_name]
+
+
+def gen_seam():
+    """Goldens of the seams (SURVEY section 8 f): DNA head, embedding hand-off, derived feature types."""
+    import types
+    from torch import Tensor
+    import torch.nn.functional as F
+
+    # --- BarcodeBERT head: execute CLIBDDNAEncoder.forward (dna_encoder.py:131-137) on a stub encoder
+    fwd = load_ref_function(f"{REF}/bioscanclip/model/dna_encoder.py", "forward", class_name="CLIBDDNAEncoder",
+                            extra_ns={"Tensor": Tensor})
+    g = torch.Generator().manual_seed(21)
+    for name, (n, t, c), scale in (("seam_softmax_mean_n3_t133_c96", (3, 133, 96), 3.0),
+                                   ("seam_softmax_mean_n2_t7_c45", (2, 7, 45), 8.0)):
+        logits = (torch.randn(n, t, c, generator=g) * scale).requires_grad_(True)
+        stub = types.SimpleNamespace(base_dna_encoder=lambda seq, _l=logits: types.SimpleNamespace(logits=_l))
+        out = fwd(stub, None)
+        gout = torch.randn(n, c, generator=g)
+        out.backward(gout)
+        save(name, {"logits": logits.detach().numpy(), "grad_out": gout.numpy()},
+             {"out": out.detach().numpy(), "grad_logits": logits.grad.numpy()},
+             {"ref": "dna_encoder.py:137 logits.softmax(dim=-1).mean(dim=1) + torch autograd"})
+
+    # --- embedding hand-off: the lines of inference_epoch.py:96-101 and :108-119 applied to two batches
+    feats = [torch.randn(5, 768, generator=g) * 3.0, torch.randn(3, 768, generator=g) * 0.01]
+    feats[1][1] = 0.0  # a zero row: F.normalize's eps clamp
+    lst = []
+    for f in feats:
+        lst.extend(F.normalize(f, dim=-1).cpu().tolist())
+    arr = np.array(lst)
+    save("seam_embed_handoff_n8_d768", {"batch0": feats[0].numpy(), "batch1": feats[1].numpy()}, {"features": arr},
+         {"ref": "inference_epoch.py:96-101,108-119"})
+
+    # --- derived feature types: execute get_features_and_label (util.py:702-742) on stubbed extraction
+    rng = np.random.default_rng(5)
+    img, dna, txt = (rng.standard_normal((6, 16)).astype(np.float32).astype(np.float64) for _ in range(3))
+    labels = [{"order": f"o{i}", "family": f"f{i}", "genus": f"g{i}", "species": f"s{i}"} for i in range(6)]
+    stub_extract = lambda *a, **k: (list(range(6)), img, dna, txt, labels)  # noqa: E731
+    gfl = load_ref_function(f"{REF}/bioscanclip/util/util.py", "get_features_and_label",
+                            extra_ns={"np": np, "get_feature_and_label": stub_extract})
+    d = gfl(None, types.SimpleNamespace(eval=lambda: None), None, for_key_set=True)
+    save("seam_derived_feature_types_n6_d16", {"image": img, "dna": dna, "text": txt},
+         {"averaged_feature": d["averaged_feature"], "concatenated_feature": d["concatenated_feature"],
+          "all_key_features": d["all_key_features"],
+          "all_key_features_label_species": np.array([l["species"] for l in d["all_key_features_label"]])},
+         {"ref": "util.py:702-742", "keys": sorted(d.keys())})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_ref_loss()
@@ -246,3 +305,4 @@ if __name__ == "__main__":
     gen_cliploss_world1(ref)
     gen_cliploss_world2()
     gen_accuracy()
+    gen_seam()
