@@ -96,7 +96,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      int64_t n, int num_kb, int npieces, int piece_w, int64_t tiles_per_split, float scale,
                      uint32_t idesc_s, uint32_t idesc_g, const float* __restrict__ rowcoef,
                      const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
-                     float* __restrict__ dxh) {
+                     float* __restrict__ dxh, int self_mask) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -353,6 +353,16 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         else if (2 * p + 1 >= nvalid) packed[p] &= 0xFFFFu;
                     }
                 }
+                if (self_mask) {  // info-NCE on one feature set: the entry (row, row) does not exist
+                    const int64_t kd = row0 + lrow - (t * PAIR_BJ + h * 128);
+                    if (kd >= 0 && kd < 128) {
+#pragma unroll
+                        for (int p = 0; p < 64; ++p) {
+                            if (2 * p == kd) packed[p] &= 0xFFFF0000u;
+                            else if (2 * p + 1 == kd) packed[p] &= 0xFFFFu;
+                        }
+                    }
+                }
                 TLAP(11);
                 // the previous G~ tile must have been consumed before it is overwritten
                 TWAIT(7, mbar_wait(g_empty, (tl & 1) ^ 1));
@@ -467,7 +477,7 @@ bool pair_backward_supported(int64_t dpad) { return dpad <= PAIR_DCH; }
 int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
-                          int fmt_bf16, float* dxh, cudaStream_t s) {
+                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % P_BK == 0 && dpad <= PAIR_DCH, "pair backward needs a padded feature dim <= 768");
     static bool attr_set = false;
@@ -497,7 +507,7 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     auto kern = fmt_bf16 ? loss_bwd_pair_kernel<true> : loss_bwd_pair_kernel<false>;
     kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
                                                piece_w, tiles_per_split, scale, idesc_s, idesc_g, rowcoef, colcoef,
-                                               gscale, weight, accumulate, dxh);
+                                               gscale, weight, accumulate, dxh, self_mask);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

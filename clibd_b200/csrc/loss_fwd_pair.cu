@@ -52,7 +52,7 @@ __device__ __forceinline__ void pair_tile_coords(int64_t t, int64_t num_mt, int6
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
 loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int64_t N,
                      int64_t row0, int64_t n, int num_kb, float scale, uint32_t idesc, float* __restrict__ rowpart,
-                     float* __restrict__ colpart) {
+                     float* __restrict__ colpart, int self_mask) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -173,7 +173,11 @@ loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             const int64_t lrow = rbase + q * 32 + lane;
             const bool row_ok = lrow < n;
             const int64_t colbase = nt * Q_TN + h * 128;
-            const bool full_tile = (rbase + 128 <= n) && (nt * Q_TN + Q_TN <= N);
+            // self_mask (info-NCE on one feature set, simclr.py:76-79): entries whose global row equals their column are
+            // excluded; only the tiles the diagonal crosses take the predicated branch
+            const int64_t grow = row0 + lrow;
+            const bool on_diag = self_mask && (row0 + rbase < colbase + 128) && (colbase < row0 + rbase + 128);
+            const bool full_tile = (rbase + 128 <= n) && (nt * Q_TN + Q_TN <= N) && !on_diag;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             float rsum = 0.f;
@@ -195,7 +199,8 @@ loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 } else {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        const bool ok = row_ok && (colbase + c * 32 + k < N);
+                        const int64_t gc = colbase + c * 32 + k;
+                        const bool ok = row_ok && (gc < N) && !(on_diag && gc == grow);
                         e[k] = ok ? ex2_approx(fmaf(__uint_as_float(v[k]), a, nb)) : 0.f;
                     }
                 }
@@ -242,7 +247,7 @@ loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 }  // namespace
 
 int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
-                        int fmt_bf16, float* rowpart, float* colpart, int num_sms, cudaStream_t s) {
+                        int fmt_bf16, float* rowpart, float* colpart, int num_sms, cudaStream_t s, int self_mask) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % Q_BK == 0, "padded feature dim must be a multiple of 64");
     CUtensorMap tm_a, tm_b;
@@ -261,7 +266,7 @@ int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t d
     const uint32_t idesc = make_idesc_f16(256, Q_TN, fmt_bf16 ? 1u : 0u);
     ProfScope prof(PROF_LOSS_FWD_TC, s);
     loss_fwd_pair_kernel<<<2 * pairs, Q_THREADS, Q_SMEM_TOTAL, s>>>(tm_a, tm_b, N, row0, n, static_cast<int>(dpad / Q_BK),
-                                                                  scale, idesc, rowpart, colpart);
+                                                                  scale, idesc, rowpart, colpart, self_mask);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

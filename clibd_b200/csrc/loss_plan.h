@@ -99,11 +99,11 @@ int launch_normalize_bwd(const NormBwdArgs& a, cudaStream_t s);
 // ---- CUDA-core fp32 path (loss_simt.cu) ---------------------------------------------
 int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* inv_a, const float* inv_b, int64_t N,
                       int64_t d, int64_t row0, int64_t n, float scale, float* rowpart, float* colpart,
-                      cudaStream_t s);
+                      cudaStream_t s, int self_mask = 0);
 // dxh[n,d] (+)= weight * sum_j e_ij (rowcoef_i + colcoef_j) yhat_j   for local rows i of x
 int simt_backward_rows(const void* x, const void* y, int dtype, const float* inv_x, const float* inv_y, int64_t N,
                        int64_t d, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
-                       float weight, int accumulate, float* dxh, cudaStream_t s);
+                       float weight, int accumulate, float* dxh, cudaStream_t s, int self_mask = 0);
 
 // ---- tcgen05 path (loss_tc.cu) --------------------------------------------------------
 int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
@@ -115,12 +115,15 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
 
 // CTA-pair forward (loss_fwd_pair.cu): 256 x 256 tiles, cta_group::2
 int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
-                        int fmt_bf16, float* rowpart, float* colpart, int num_sms, cudaStream_t s);
+                        int fmt_bf16, float* rowpart, float* colpart, int num_sms, cudaStream_t s, int self_mask = 0);
 // CTA-pair variant (loss_bwd_pair.cu): whole feature dimension per pair, S computed once per sweep; dpad <= 768
 bool pair_backward_supported(int64_t dpad);
 int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
-                          int fmt_bf16, float* dxh, cudaStream_t s);
+                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask = 0);
+// self_mask = 1 (all four launchers above): the operands are the SAME feature set and the entries whose global row
+// equals their column are excluded from the sums (SimCLR info-NCE, bioscanclip/util/simclr.py:76-79)
+int tc_num_sms();
 
 }  // namespace clibd

@@ -19,7 +19,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float* __restrict__ inv_a,
                 const float* __restrict__ inv_b, int64_t N, int64_t d, int64_t row0, int64_t n, float scale,
-                float* __restrict__ rowpart, float* __restrict__ colpart) {
+                float* __restrict__ rowpart, float* __restrict__ colpart, int self_mask) {
     __shared__ float As[KT][T64 + 1];
     __shared__ float Bs[KT][T64 + 1];
     __shared__ float red[T64][17];
@@ -68,7 +68,8 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const bool valid = (lrow0 + ty * 4 + i < n) && (col0 + tx * 4 + j < N);
+            const bool valid = (lrow0 + ty * 4 + i < n) && (col0 + tx * 4 + j < N) &&
+                               !(self_mask && row0 + lrow0 + ty * 4 + i == col0 + tx * 4 + j);
             const float e = valid ? expf(fmaf(scale, acc[i][j], -scale)) : 0.f;
             rsum[i] += e;
             csum[j] += e;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256)
 simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ inv_x,
                 const float* __restrict__ inv_y, int64_t N, int64_t d, int64_t row0, int64_t n, float scale,
                 const float* __restrict__ rowcoef, const float* __restrict__ colcoef, float weight, int accumulate,
-                float* __restrict__ dxh) {
+                float* __restrict__ dxh, int self_mask) {
     __shared__ float Xs[BR][BJ + 1];
     __shared__ float Ys[BJ][BJ + 1];
     __shared__ float Gs[BR][BJ + 1];
@@ -149,7 +150,8 @@ simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* _
             for (int c = 0; c < 4; ++c) {
                 const int64_t gj = j0 + scol + c;
                 float g = 0.f;
-                if (lr < n && gj < N) g = expf(fmaf(scale, s4[c], -scale)) * (rc + colcoef[gj]);
+                if (lr < n && gj < N && !(self_mask && row0 + lr == gj))
+                    g = expf(fmaf(scale, s4[c], -scale)) * (rc + colcoef[gj]);
                 Gs[srow][scol + c] = g;
             }
         }
@@ -200,23 +202,24 @@ simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* _
 
 int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* inv_a, const float* inv_b, int64_t N,
                       int64_t d, int64_t row0, int64_t n, float scale, float* rowpart, float* colpart,
-                      cudaStream_t s) {
+                      cudaStream_t s, int self_mask) {
     if (n == 0 || N == 0) return 0;
     dim3 grid(static_cast<unsigned>(ceil_div(N, T64)), static_cast<unsigned>(ceil_div(n, T64)));
     DISPATCH_DTYPE(dtype, (simt_fwd_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(xa), static_cast<const T*>(xb),
-                                                                  inv_a, inv_b, N, d, row0, n, scale, rowpart, colpart)));
+                                                                  inv_a, inv_b, N, d, row0, n, scale, rowpart, colpart,
+                                                                  self_mask)));
     CLIBD_KERNEL_CHECK();
     return 0;
 }
 
 int simt_backward_rows(const void* x, const void* y, int dtype, const float* inv_x, const float* inv_y, int64_t N,
                        int64_t d, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
-                       float weight, int accumulate, float* dxh, cudaStream_t s) {
+                       float weight, int accumulate, float* dxh, cudaStream_t s, int self_mask) {
     if (n == 0 || N == 0) return 0;
     dim3 grid(static_cast<unsigned>(ceil_div(n, BR)), static_cast<unsigned>(ceil_div(d, 256 * DQ)));
     DISPATCH_DTYPE(dtype, (simt_bwd_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(y),
                                                                   inv_x, inv_y, N, d, row0, n, scale, rowcoef, colcoef,
-                                                                  weight, accumulate, dxh)));
+                                                                  weight, accumulate, dxh, self_mask)));
     CLIBD_KERNEL_CHECK();
     return 0;
 }
