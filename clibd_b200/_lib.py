@@ -39,6 +39,8 @@ SIGNATURES = {
     "clibd_softmax_mean_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
     "clibd_softmax_mean_forward": (_INT, [_P, _INT, _I64, _I64, _I64, _P, _P, _I64, _P]),
     "clibd_softmax_mean_backward": (_INT, [_P, _P, _INT, _I64, _I64, _I64, _P, _P]),
+    "clibd_infonce_forward": (_INT, [_P, _INT, _P, _I64, _I64, _F, _INT, _P, _I64, _P, _P, _P]),
+    "clibd_infonce_backward": (_INT, [_P, _INT, _P, _I64, _I64, _F, _INT, _P, _I64, _F, _P, _P, _P]),
 }
 
 _lib = None
@@ -77,7 +79,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.clibd_abi_version() != 3:
+    if lib.clibd_abi_version() != 4:
         raise RuntimeError("clibd_b200: ABI version mismatch")
     _lib = lib
     return lib

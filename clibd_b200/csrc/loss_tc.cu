@@ -541,6 +541,8 @@ int num_sms() {
 
 }  // namespace
 
+int tc_num_sms() { return num_sms(); }
+
 int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,
                     int fmt_bf16, float* rowpart, float* colpart, cudaStream_t s) {
     if (n == 0 || N == 0) return 0;

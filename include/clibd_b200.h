@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 3
+#define CLIBD_ABI_VERSION 4
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -147,6 +147,22 @@ int clibd_softmax_mean_forward(const void* logits, int dtype, int64_t n, int64_t
                                void* scratch, int64_t scratch_bytes, clibd_stream_t stream);
 int clibd_softmax_mean_backward(const void* logits, const void* grad_out, int dtype, int64_t n, int64_t tokens,
                                 int64_t classes, void* grad_logits, clibd_stream_t stream);
+
+/* ---- SimCLR info-NCE (SURVEY.md section 8 f, rank 4) --------------------------------------------
+ * Replaces SimCLR.info_nce_loss + nn.CrossEntropyLoss (bioscanclip/util/simclr.py:64-92, 118-119) for
+ * n_views = 2: z [m, d] in `dtype`, rows i and (i + m/2) mod m are the two views of one image;
+ * loss = mean_i [ LSE_{j != i}(cos_ij / tau) - cos_{i,partner(i)} / tau ].  The m x m logits are never
+ * materialised (same fused kernels as the contrastive loss, diagonal entries excluded).
+ * inv_norm: [m] from clibd_row_inv_norm; scratch: clibd_loss_scratch_bytes(m, m, d, path) bytes, kept from
+ * forward to backward; rowsum: [m] float32 output (sum_{j != i} exp((cos_ij - 1) / tau), kept for the caller's
+ * diagnostics); inv_temperature = 1 / tau in (0, 43].  tcgen05 paths need d <= 768.
+ * Backward: dz [m, d] in `dtype` receives grad_scale * grad_scale_dev[0] * dL/dz (device scalar optional). */
+int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64_t m, int64_t d,
+                          float inv_temperature, int path, void* scratch, int64_t scratch_bytes, float* rowsum,
+                          float* loss_out, clibd_stream_t stream);
+int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int64_t m, int64_t d,
+                           float inv_temperature, int path, void* scratch, int64_t scratch_bytes, float grad_scale,
+                           const float* grad_scale_dev, void* dz, clibd_stream_t stream);
 
 #ifdef __cplusplus
 }

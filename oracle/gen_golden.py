@@ -298,6 +298,32 @@ def gen_seam():
          {"ref": "util.py:702-742", "keys": sorted(d.keys())})
 
 
+def gen_info_nce():
+    """SimCLR info-NCE goldens: execute SimCLR.info_nce_loss (simclr.py:64-92) from the reference source on a
+    stub `self`, then the trainer's criterion (nn.CrossEntropyLoss, simclr.py:62,119) and torch autograd."""
+    import types
+    import torch.nn.functional as F
+    fn = load_ref_function(f"{REF}/bioscanclip/util/simclr.py", "info_nce_loss", class_name="SimCLR",
+                           extra_ns={"torch": torch, "F": F})
+    g = torch.Generator().manual_seed(33)
+    for name, (B, d, tau, gm, corr) in (("infonce_b64_d768_t0.07", (64, 768, 0.07, 1.0, 0.0)),
+                                        ("infonce_b45_d40_t0.2_views_correlated", (45, 40, 0.2, 1.0, 0.8)),
+                                        ("infonce_b16_d96_t0.07_gradscale65536", (16, 96, 0.07, 65536.0, 0.5))):
+        base = torch.randn(B, d, generator=g)
+        v1 = corr * base + (1 - corr) * torch.randn(B, d, generator=g)
+        v2 = corr * base + (1 - corr) * torch.randn(B, d, generator=g)
+        feats = (torch.cat([v1, v2], 0) * 2.5).requires_grad_(True)
+        stub = types.SimpleNamespace(
+            args=types.SimpleNamespace(model_config=types.SimpleNamespace(batch_size=B, n_views=2, temperature=tau)),
+            device="cpu")
+        logits, labels = fn(stub, feats)
+        loss = torch.nn.CrossEntropyLoss()(logits, labels)
+        (loss * gm).backward()
+        save(name, {"features": feats.detach().numpy()},
+             {"loss": np.float64(loss.item()), "grad": feats.grad.numpy(), "logits": logits.detach().numpy()},
+             {"ref": "simclr.py:64-92,119", "batch_size": B, "n_views": 2, "temperature": tau, "grad_mult": gm})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_ref_loss()
@@ -306,3 +332,4 @@ if __name__ == "__main__":
     gen_cliploss_world2()
     gen_accuracy()
     gen_seam()
+    gen_info_nce()

@@ -8,6 +8,9 @@ Restates /root/reference/bioscanclip/model/loss_func.py:
   * nn.CrossEntropyLoss() with float [N,N] targets (train_cl.py:260,262)
                                                            -> soft_target_ce()
 
+and /root/reference/bioscanclip/util/simclr.py:
+  * SimCLR.info_nce_loss + criterion  simclr.py:64-92,119  -> info_nce()
+
 Parity PINNED: tests/test_oracle_loss.py checks every function here against
 tests/golden/loss_*.npz, which oracle/gen_golden.py produced by running the
 reference's own PyTorch code (imported from /root/reference) on seeded inputs.
@@ -235,3 +238,40 @@ def row_block_fwd_bwd(features, labels, logit_scale, r0, r1, dtype=np.float32):
             dB = G.T @ A
             acc += float(dA[0, 0]) + float(dB[0, 0])
     return acc
+
+
+def info_nce(features, batch_size, n_views=2, temperature=0.07, dtype=np.float64):
+    """SimCLR.info_nce_loss followed by nn.CrossEntropyLoss()(logits, zeros) (simclr.py:64-92, 119), restated
+    step by step on the materialised matrices, plus the analytic gradient w.r.t. the un-normalised features.
+
+    Returns {"loss", "grad", "logits"}: logits [M, M-1] are the reference's re-ordered logits (positives
+    first, then the negatives in column order), before the division by the temperature is undone."""
+    x = np.asarray(features, dtype=dtype)
+    M = x.shape[0]
+    ids = np.concatenate([np.arange(batch_size) for _ in range(n_views)])           # simclr.py:66-67
+    lab = (ids[None, :] == ids[:, None])                                             # :69
+    xh, nrm = l2_normalize(x)                                                        # :72
+    sim = xh @ xh.T                                                                  # :74
+    off = ~np.eye(M, dtype=bool)                                                     # :77
+    lab_o = lab[off].reshape(M, M - 1)                                               # :78
+    sim_o = sim[off].reshape(M, M - 1)                                               # :79
+    pos = sim_o[lab_o].reshape(M, -1)                                                # :83
+    neg = sim_o[~lab_o].reshape(M, -1)                                               # :86
+    logits = np.concatenate([pos, neg], axis=1) / temperature                        # :88,91
+    m = logits.max(axis=1, keepdims=True)
+    lse = m + np.log(np.exp(logits - m).sum(axis=1, keepdims=True))
+    loss = float((lse[:, 0] - logits[:, 0]).mean())                                  # CE with target class 0
+    # gradient: dL/dlogits = (softmax - onehot_0) / M, scattered back to the [M, M] similarity matrix
+    p = np.exp(logits - lse)
+    p[:, 0] -= 1.0
+    p /= M
+    g_pos, g_neg = p[:, :pos.shape[1]], p[:, pos.shape[1]:]
+    g_o = np.zeros((M, M - 1), dtype=dtype)
+    g_o[lab_o] = g_pos.reshape(-1)
+    g_o[~lab_o] = g_neg.reshape(-1)
+    G = np.zeros((M, M), dtype=dtype)
+    G[off] = g_o.reshape(-1)
+    G /= temperature
+    dxh = G @ xh + G.T @ xh                                                          # sim = xh xh^T
+    grad = (dxh - xh * (xh * dxh).sum(axis=1, keepdims=True)) / nrm                  # F.normalize backward
+    return {"loss": loss, "grad": grad, "logits": logits}

@@ -1,0 +1,110 @@
+"""GPU parity tests of the fused SimCLR info-NCE loss (clibd_b200.info_nce_loss, through the C ABI) against
+(a) goldens produced by executing the reference's SimCLR.info_nce_loss source + CrossEntropyLoss and
+(b) the CPU oracle (oracle/loss_oracle.py:info_nce)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle as lo
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = ("infonce_b64_d768_t0.07", "infonce_b45_d40_t0.2_views_correlated", "infonce_b16_d96_t0.07_gradscale65536")
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _run(feats, B, tau, operands=None, grad_mult=1.0):
+    import clibd_b200 as cb
+    leaf = feats.clone().requires_grad_(True)
+    loss = cb.info_nce_loss(leaf, B, 2, tau, tensor_core_operands=operands)
+    (loss * grad_mult).backward()
+    torch.cuda.synchronize()
+    return float(loss), leaf.grad.float().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_fp32_path_matches_reference_golden(name):
+    """fp32 CUDA-core path vs the reference's own code; tolerance 1e-5 (north_star, fp32)."""
+    g = _golden.load(name)
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(g.inputs["features"]).to(dev)
+    loss, grad = _run(x, g.meta["batch_size"], g.meta["temperature"], grad_mult=g.meta["grad_mult"])
+    ref = float(g.outputs["loss"])
+    assert abs(loss - ref) <= 1e-5 * abs(ref)
+    assert _rel(grad, g.outputs["grad"]) < 3e-5
+
+
+@pytest.mark.parametrize("operands", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", GOLDENS[:2])
+def test_tensor_core_path_matches_reference_golden(name, operands):
+    """tcgen05 paths (16-bit operands, fp32 accumulate) vs the reference; tolerance 1e-3 (north_star, bf16)."""
+    g = _golden.load(name)
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(g.inputs["features"]).to(dev)
+    loss, grad = _run(x, g.meta["batch_size"], g.meta["temperature"], operands=operands)
+    ref = float(g.outputs["loss"])
+    assert abs(loss - ref) <= 1e-3 * abs(ref)
+    assert _rel(grad, g.outputs["grad"]) < 2e-3
+
+
+@pytest.mark.parametrize("operands,tol", [("fp32", 2e-5), ("bf16", 2e-3), ("fp16", 1e-3)])
+@pytest.mark.parametrize("B,d,tau,corr", [
+    (512, 768, 0.07, 0.7),    # diagonal crosses four 256 x 256 tiles
+    (333, 200, 0.1, 0.5),     # ragged: M = 666 not a multiple of 128, d not a multiple of 64
+    (65, 64, 0.5, 0.0),       # partner rows straddle the first tile boundary
+])
+def test_paths_match_oracle(B, d, tau, corr, operands, tol):
+    gen = torch.Generator().manual_seed(B + d)
+    base = torch.randn(B, d, generator=gen)
+    v = [corr * base + (1 - corr) * torch.randn(B, d, generator=gen) for _ in range(2)]
+    x = torch.cat(v, 0)
+    if operands != "fp32":
+        x = x.bfloat16().float() if operands == "bf16" else x.half().float()
+    ref = lo.info_nce(x.numpy(), B, 2, tau)
+    dt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[operands]
+    loss, grad = _run(x.to("cuda:0").to(dt), B, tau)
+    assert abs(loss - ref["loss"]) <= max(tol, 1e-5) * abs(ref["loss"])
+    assert _rel(grad, ref["grad"]) < 2 * tol
+
+
+def test_large_batch_properties():
+    """M = 16384 (BASELINE-scale rows, oracle too slow): size-independent properties.
+    (1) x_i . dL/dx_i = 0 (the loss is invariant to the scale of every row);
+    (2) swapping the two views permutes the gradient rows and keeps the loss;
+    (3) the gradient is linear in grad_output; (4) the tcgen05 loss agrees with the fp32 CUDA-core path."""
+    B, d, tau = 8192, 768, 0.07
+    gen = torch.Generator().manual_seed(5)
+    base = torch.randn(B, d, generator=gen)
+    x = torch.cat([0.6 * base + 0.4 * torch.randn(B, d, generator=gen) for _ in range(2)], 0).bfloat16().to("cuda:0")
+    loss, grad = _run(x, B, tau)
+    xf = x.float().cpu().numpy()
+    row_dot = np.abs((xf * grad).sum(1))
+    assert row_dot.max() <= 2e-2 * np.abs(xf).max() * np.abs(grad).sum(1).max()
+    swapped = torch.cat([x[B:], x[:B]], 0)
+    loss_s, grad_s = _run(swapped, B, tau)
+    assert abs(loss_s - loss) <= 1e-5 * abs(loss)   # other summation order
+    assert _rel(np.concatenate([grad_s[B:], grad_s[:B]]), grad) < 1e-3  # bf16 gradient storage
+    _, grad3 = _run(x, B, tau, grad_mult=3.0)
+    assert _rel(grad3, 3.0 * grad) < 1e-2  # bf16 output rounding
+    loss32, grad32 = _run(x.float(), B, tau, operands="fp32")
+    assert abs(loss - loss32) <= 1e-3 * abs(loss32)
+    assert _rel(grad, grad32) < 5e-3  # bf16 operands + bf16 gradient storage vs exact fp32
+
+
+def test_argument_errors():
+    import clibd_b200 as cb
+    x = torch.randn(8, 16, device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        cb.info_nce_loss(x, 2, n_views=4)
+    with pytest.raises(ValueError):
+        cb.info_nce_loss(x, 3, 2)
+    with pytest.raises(RuntimeError):
+        cb.info_nce_loss(x.cpu(), 4, 2)
+    with pytest.raises(ValueError):
+        cb.info_nce_loss(x, 4, 2, temperature=0.01)  # 1/tau > 43: outside the fixed-shift softmax range

@@ -69,3 +69,42 @@ def test_pair_filter_quirks():
     assert lo.ordered_pairs(3, no_image_text_loss=True) == [(0, 1), (1, 0), (1, 2), (2, 1)]
     assert lo.ordered_pairs(2, bind_to="text") == []  # index 2 does not exist in a 2-entry list
     assert lo.ordered_pairs(2, no_image_text_loss=True) == [(0, 1), (1, 0)]
+
+
+INFONCE_GOLDENS = ("infonce_b64_d768_t0.07", "infonce_b45_d40_t0.2_views_correlated",
+                   "infonce_b16_d96_t0.07_gradscale65536")
+
+
+@pytest.mark.parametrize("name", INFONCE_GOLDENS)
+def test_info_nce_oracle_matches_reference_golden(name):
+    """oracle info_nce() vs SimCLR.info_nce_loss + CrossEntropyLoss executed from the reference source."""
+    g = _golden.load(name)
+    out = lo.info_nce(g.inputs["features"], g.meta["batch_size"], g.meta["n_views"], g.meta["temperature"])
+    np.testing.assert_allclose(out["logits"], g.outputs["logits"], rtol=2e-5, atol=2e-5)
+    assert out["loss"] == pytest.approx(float(g.outputs["loss"]), rel=2e-6)
+    ref = g.outputs["grad"] / g.meta["grad_mult"]
+    err = np.linalg.norm(out["grad"] - ref) / np.linalg.norm(ref)
+    assert err < 2e-5, err  # the golden is torch float32 autograd
+
+
+@pytest.mark.parametrize("name", INFONCE_GOLDENS)
+def test_info_nce_fused_formulation_matches_oracle(name):
+    """The restatement the CUDA path uses (csrc/infonce.cu): fixed-shift exponentials with the diagonal
+    dropped, row sums r_i, loss = mean(s + ln r_i - s zhat_i.zhat_p(i)),
+    dzhat_k = (s/M) [sum_{j != k} e_kj (1/r_k + 1/r_j) zhat_j - 2 zhat_p(k)]."""
+    g = _golden.load(name)
+    x = g.inputs["features"].astype(np.float64)
+    B, s = g.meta["batch_size"], 1.0 / g.meta["temperature"]
+    M = x.shape[0]
+    xh, nrm = lo.l2_normalize(x)
+    e = np.exp(s * (xh @ xh.T) - s)
+    np.fill_diagonal(e, 0.0)
+    r = e.sum(axis=1)
+    partner = np.roll(xh, -B, axis=0)  # row k -> zhat[(k + B) mod M]
+    loss = (s + np.log(r)).mean() - s * (xh * partner).sum() / M
+    coef = e * (1.0 / r[:, None] + 1.0 / r[None, :])
+    dxh = (s / M) * (coef @ xh - 2.0 * partner)
+    grad = (dxh - xh * (xh * dxh).sum(axis=1, keepdims=True)) / nrm
+    ref = lo.info_nce(x, B, 2, g.meta["temperature"])
+    assert loss == pytest.approx(ref["loss"], rel=1e-12)
+    assert np.linalg.norm(grad - ref["grad"]) / np.linalg.norm(ref["grad"]) < 1e-11
