@@ -22,11 +22,13 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__global__ void infonce_prepare_kernel(int64_t M, int32_t* __restrict__ rep, float* __restrict__ cnt) {
+__global__ void infonce_prepare_kernel(int64_t M, int64_t B, int32_t* __restrict__ rep, float* __restrict__ cnt,
+                                       int32_t* __restrict__ partner) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < M) {
         rep[i] = static_cast<int32_t>(i);
         cnt[i] = 1.f;
+        partner[i] = static_cast<int32_t>((i + B) % M);  // the row's one positive column
     }
 }
 
@@ -45,8 +47,8 @@ __global__ void infonce_partner_kernel(const T* __restrict__ z, const float* __r
 }
 
 struct Views {
-    int32_t* rep;
-    float *cnt, *gscale, *P, *u, *v, *rowpart, *colpart, *posrow, *dots, *dxh;
+    int32_t *rep, *partner;
+    float *cnt, *gscale, *P, *u, *v, *rowpart, *colpart, *posrow, *dots, *dxh, *ccS, *lam2;
     double* red;
     void *xh, *xhT;
 };
@@ -55,6 +57,9 @@ Views carve(void* scratch, const LossPlan& plan) {
     Views w;
     w.rep = at<int32_t>(scratch, plan.off_rep);
     w.cnt = at<float>(scratch, plan.off_cnt);
+    w.partner = at<int32_t>(scratch, plan.off_class_lo);
+    w.ccS = at<float>(scratch, plan.off_ccS);
+    w.lam2 = at<float>(scratch, plan.off_lam2);
     w.gscale = at<float>(scratch, plan.off_gscale);
     w.P = at<float>(scratch, plan.off_Q[0]);
     w.u = at<float>(scratch, plan.off_u);
@@ -105,7 +110,7 @@ int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64
     const Views w = carve(scratch, plan);
     const int64_t B = M / 2;
     const float scale = inv_temperature;
-    infonce_prepare_kernel<<<ceil_div(M, kThreads), kThreads, 0, stream>>>(M, w.rep, w.cnt);
+    infonce_prepare_kernel<<<ceil_div(M, kThreads), kThreads, 0, stream>>>(M, B, w.rep, w.cnt, w.partner);
     CLIBD_KERNEL_CHECK();
     if ((rc = launch_gscale(w.cnt, M, path, w.gscale, stream))) return rc;
     {
@@ -154,10 +159,14 @@ int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int6
     CLIBD_REQUIRE(dz != nullptr, "null output pointer");
     const Views w = carve(scratch, plan);
     const float scale = inv_temperature;
-    if (path != PATH_SIMT_F32) {
+    const bool tc = path != PATH_SIMT_F32;
+    if (tc) {
         const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
-        rc = tc_backward_rows_pair(w.xh, w.xh, w.xhT, M, plan.npad, d, plan.dpad, 0, M, scale, w.u, w.v, w.gscale, 1.0f,
-                                   /*accumulate=*/0, plan.jsplit, fmt_bf16, w.dxh, stream, /*self_mask=*/1);
+        // lam2_i ~ G~ at the partner column: the epilogue emits G~ - lam2 there (columns stay in input order)
+        if ((rc = launch_sweep_prep(w.u, w.v, nullptr, w.cnt, w.posrow, M, 0, M, scale, w.ccS, w.lam2, stream))) return rc;
+        rc = tc_backward_rows_pair(w.xh, w.xh, w.xhT, M, plan.npad, d, plan.dpad, 0, M, scale, w.u, w.ccS, w.gscale, 1.0f,
+                                   /*accumulate=*/0, plan.jsplit, fmt_bf16, w.dxh, stream, /*self_mask=*/1, w.partner,
+                                   w.cnt, w.lam2);
     } else {
         rc = simt_backward_rows(z, z, dtype, inv_norm, inv_norm, M, d, 0, M, scale, w.u, w.v, 1.0f, /*accumulate=*/0,
                                 w.dxh, stream, /*self_mask=*/1);
@@ -174,6 +183,7 @@ int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int6
     a.Qp[1] = nullptr;
     a.wp[0] = 1.f;
     a.wp[1] = 0.f;
+    a.lam2[0] = tc ? w.lam2 : nullptr;
     a.N = M;
     a.d = d;
     a.row0 = 0;

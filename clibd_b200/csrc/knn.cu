@@ -767,9 +767,7 @@ int run_exhaustive(const float* q32, const int32_t* qsel, int64_t nq_total, cons
 
 }  // namespace
 
-// declared in loss_support.cu; reused here with inv == nullptr (rows already normalised)
-int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
-                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s);
+// launch_make_operands (loss_plan.h, loss_support.cu) is reused here with inv == nullptr (rows already normalised)
 
 }  // namespace clibd
 

@@ -86,6 +86,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
         p.off_dxh[m] = take(sizeof(float) * p.jsplit * n * d);
         if (tc) {
             p.off_xh[m] = take(2 * static_cast<size_t>(N) * p.dpad);
+            p.off_xhS[m] = take(2 * static_cast<size_t>(N) * p.dpad);
             p.off_xhT[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad);
         }
     }
@@ -94,6 +95,11 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
     p.off_rowpart = take(sizeof(float) * p.row_parts * n);
     p.off_colpart = take(sizeof(float) * p.col_parts * N);
     p.off_posrow = take(sizeof(float) * n);
+    p.off_cstart = take(sizeof(int32_t) * N);
+    p.off_class_lo = take(sizeof(int32_t) * N);
+    p.off_ccS = take(sizeof(float) * N);
+    p.off_posrow2 = take(sizeof(float) * 6 * n);
+    p.off_lam2 = take(sizeof(float) * 6 * n);
     p.off_dots = take(sizeof(float) * 3 * n);
     p.off_red = take(sizeof(double) * 512);
     const int64_t H = label_hash_slots(N);
@@ -217,6 +223,9 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
     ls.sort_tmp_bytes = plan.sort_tmp_bytes;
     if ((rc = launch_label_stats(labels, N, rep, cnt, ls, stream))) return rc;
     if ((rc = launch_gscale(cnt, N, path, gscale, stream))) return rc;
+    if ((rc = launch_class_ranges(ls.skey, rep, N, at<int32_t>(scratch, plan.off_cstart),
+                                  at<int32_t>(scratch, plan.off_class_lo), stream)))
+        return rc;
     bool used[3] = {false, false, false};
     for (int p = 0; p < 3; ++p)
         if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
@@ -225,14 +234,16 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
         if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], ls.skey, ls.sidx, cnt, N, d, at<float>(scratch, plan.off_Q[m]), stream)))
             return rc;
         if (tc) {
+            // row operand in input order, column operands (xhS, xhT) in class-sorted order
             if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16,
-                                           at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream)))
+                                           at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream,
+                                           ls.sidx, at<void>(scratch, plan.off_xhS[m]))))
                 return rc;
         }
     }
     float* rowpart = at<float>(scratch, plan.off_rowpart);
     float* colpart = at<float>(scratch, plan.off_colpart);
-    float* posrow = at<float>(scratch, plan.off_posrow);
+    float* posrow2 = at<float>(scratch, plan.off_posrow2);
     double* red = at<double>(scratch, plan.off_red);
     for (int p = 0; p < 3; ++p) {
         if (pair_weight[p] == 0.f) {
@@ -241,7 +252,7 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
         }
         const int a = kPairA[p], b = kPairB[p];
         if (tc) {
-            rc = tc_forward_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xh[b]), N, plan.dpad, row0,
+            rc = tc_forward_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]), N, plan.dpad, row0,
                                  n, logit_scale, fmt_bf16, rowpart, colpart, stream);
         } else {
             rc = simt_forward_pair(x[a], x[b], dtype, inv_norm[a], inv_norm[b], N, d, row0, n, logit_scale, rowpart,
@@ -249,9 +260,16 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
         }
         if (rc) return rc;
         if ((rc = launch_reduce_parts(rowpart, plan.row_parts, n, n, rowsum + p * N + row0, stream))) return rc;
-        if ((rc = launch_reduce_parts(colpart, plan.col_parts, N, N, colsum + p * N, stream))) return rc;
+        // the tcgen05 column sums come out in class-sorted column order: scatter them back to input order
+        if ((rc = launch_reduce_parts(colpart, plan.col_parts, N, N, colsum + p * N, stream, tc ? ls.sidx : nullptr)))
+            return rc;
+        // per-row positive dot products of both directions (direction 0 also gives the loss's positive term)
+        float* posrow = posrow2 + (2 * p) * n;
         if ((rc = launch_pos_rows(x[a], dtype, inv_norm[a], at<float>(scratch, plan.off_Q[b]), rep, d, row0, n, posrow,
                                   stream)))
+            return rc;
+        if ((rc = launch_pos_rows(x[b], dtype, inv_norm[b], at<float>(scratch, plan.off_Q[a]), rep, d, row0, n,
+                                  posrow + n, stream)))
             return rc;
         if ((rc = launch_sum_to_double(posrow, n, 1.0, red, pos + p, stream))) return rc;
     }
@@ -285,39 +303,54 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     const float* gscale = at<float>(scratch, plan.off_gscale);
     const float* u = at<float>(scratch, plan.off_u);
     const float* v = at<float>(scratch, plan.off_v);
+    const float* cnt = at<float>(scratch, plan.off_cnt);
+    const int32_t* sidx = at<int32_t>(scratch, plan.off_sidx);
+    const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
+    float* ccS = at<float>(scratch, plan.off_ccS);
     float* dots = at<float>(scratch, plan.off_dots);
+    const bool use_pair = tc && pair_backward_supported(plan.dpad) && !std::getenv("CLIBD_BWD_SINGLE");
     double* red = at<double>(scratch, plan.off_red);
     int n_mod_used = 0;
     for (int m = 0; m < 3; ++m) {
         // ordered sweeps that write rows of modality m: for every weighted pair containing m
         int npart = 0;
         const float* Qp[2] = {nullptr, nullptr};
+        const float* lam[2] = {nullptr, nullptr};
         float wp[2] = {0.f, 0.f};
         float* dxh = at<float>(scratch, plan.off_dxh[m]);
         for (int p = 0; p < 3; ++p) {
             if (pair_weight[p] == 0.f) continue;
-            int other;
+            int other, dir;
             const float *rowcoef, *colcoef;
             if (kPairA[p] == m) {          // m indexes the rows of S_p
                 other = kPairB[p];
+                dir = 0;
                 rowcoef = u + p * N;
                 colcoef = v + p * N;
             } else if (kPairB[p] == m) {   // m indexes the columns of S_p: sweep S_p^T
                 other = kPairA[p];
+                dir = 1;
                 rowcoef = v + p * N;
                 colcoef = u + p * N;
             } else {
                 continue;
             }
-            if (tc && pair_backward_supported(plan.dpad) && !std::getenv("CLIBD_BWD_SINGLE")) {
-                rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xh[other]),
+            float* lam2 = use_pair ? at<float>(scratch, plan.off_lam2) + (2 * p + dir) * n : nullptr;
+            if (tc) {
+                // column coefficients in the class-sorted column order; lam2 of this sweep's rows
+                if ((rc = launch_sweep_prep(rowcoef, colcoef, sidx, cnt, at<float>(scratch, plan.off_posrow2) + (2 * p + dir) * n,
+                                            N, row0, n, logit_scale, ccS, lam2, stream)))
+                    return rc;
+            }
+            if (use_pair) {
+                rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhS[other]),
                                            at<void>(scratch, plan.off_xhT[other]), N, plan.npad, d, plan.dpad, row0, n,
-                                           logit_scale, rowcoef, colcoef, gscale, pair_weight[p], npart > 0,
-                                           plan.jsplit, fmt_bf16, dxh, stream);
+                                           logit_scale, rowcoef, ccS, gscale, pair_weight[p], npart > 0,
+                                           plan.jsplit, fmt_bf16, dxh, stream, /*self_mask=*/0, class_lo, cnt, lam2);
             } else if (tc) {
-                rc = tc_backward_rows(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xh[other]),
+                rc = tc_backward_rows(at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhS[other]),
                                       at<void>(scratch, plan.off_xhT[other]), N, plan.npad, d, plan.dpad, row0, n,
-                                      logit_scale, rowcoef, colcoef, gscale, pair_weight[p], npart > 0, plan.jsplit,
+                                      logit_scale, rowcoef, ccS, gscale, pair_weight[p], npart > 0, plan.jsplit,
                                       fmt_bf16, dxh, stream);
             } else {
                 rc = simt_backward_rows(x[m], x[other], dtype, inv_norm[m], inv_norm[other], N, d, row0, n, logit_scale,
@@ -325,6 +358,7 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
             }
             if (rc) return rc;
             Qp[npart] = at<float>(scratch, plan.off_Q[other]);
+            lam[npart] = lam2;
             wp[npart] = pair_weight[p];
             ++npart;
         }
@@ -340,6 +374,8 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
         a.Qp[1] = Qp[1];
         a.wp[0] = wp[0];
         a.wp[1] = wp[1];
+        a.lam2[0] = lam[0];
+        a.lam2[1] = lam[1];
         a.N = N;
         a.d = d;
         a.row0 = row0;

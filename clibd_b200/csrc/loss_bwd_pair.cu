@@ -96,7 +96,8 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      int64_t n, int num_kb, int npieces, int piece_w, int64_t tiles_per_split, float scale,
                      uint32_t idesc_s, uint32_t idesc_g, const float* __restrict__ rowcoef,
                      const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
-                     float* __restrict__ dxh, int self_mask) {
+                     float* __restrict__ dxh, int self_mask, const int32_t* __restrict__ pos_lo,
+                     const float* __restrict__ pos_cnt, const float* __restrict__ lam2) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -307,6 +308,16 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const uint32_t st_empty_l = mapa_u32(smem_u32(st_empty), 0);
             const uint32_t g_full_l = mapa_u32(smem_u32(g_full), 0);
             const uint32_t rowaddr = smem_u32(gbuf) + (2 * h) * P_XKB_BYTES + rloc * 128;
+            // positives of this row: columns [plo, plo + plen) (the column operand is class-sorted); there the
+            // epilogue emits G~ - lam2 so that the 16-bit rounding acts on the small difference when G~ -> 2 T
+            // (the fp32 class-sum term of normalize_bwd carries the remaining 2 - lam2)
+            int plo = 0, plen = 0;
+            float l2g = 0.f;
+            if (lam2 != nullptr && lrow < n) {
+                plo = pos_lo[row0 + lrow];
+                plen = static_cast<int>(pos_cnt[row0 + lrow]);
+                l2g = lam2[lrow] * gs;
+            }
             // Column coefficients: lane l keeps those of columns l, 32+l, 64+l, 96+l of its half of the tile in
             // registers (fetched one tile ahead) and the warp broadcasts them with shuffles -- no shared memory.
             auto load_cc = [&](int64_t t, float (&dst)[4]) {
@@ -338,13 +349,28 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 if (lane == 0) mbar_arrive_cluster(st_empty_l);
                 TLAP(10);
                 uint32_t packed[64];
+                // first column of this lane's half tile relative to the row's positive range
+                const int prel = static_cast<int>(t * PAIR_BJ + h * 128) - plo;
+                if (__any_sync(0xffffffffu, prel > -128 && prel < plen)) {  // rare: some row of the warp has positives here
 #pragma unroll
-                for (int k = 0; k < 128; k += 2) {
-                    const float c0 = __shfl_sync(0xffffffffu, ccr[k >> 5], k & 31);
-                    const float c1 = __shfl_sync(0xffffffffu, ccr[k >> 5], (k & 31) + 1);
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(v[k]), a, nb));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), a, nb));
-                    packed[k / 2] = pack2<BF16>(e0 * (rcg + c0), e1 * (rcg + c1));
+                    for (int k = 0; k < 128; k += 2) {
+                        const float c0 = __shfl_sync(0xffffffffu, ccr[k >> 5], k & 31);
+                        const float c1 = __shfl_sync(0xffffffffu, ccr[k >> 5], (k & 31) + 1);
+                        const float e0 = ex2_approx(fmaf(__uint_as_float(v[k]), a, nb));
+                        const float e1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), a, nb));
+                        const float s0 = static_cast<unsigned>(prel + k) < static_cast<unsigned>(plen) ? l2g : 0.f;
+                        const float s1 = static_cast<unsigned>(prel + k + 1) < static_cast<unsigned>(plen) ? l2g : 0.f;
+                        packed[k / 2] = pack2<BF16>(fmaf(e0, rcg + c0, -s0), fmaf(e1, rcg + c1, -s1));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 128; k += 2) {
+                        const float c0 = __shfl_sync(0xffffffffu, ccr[k >> 5], k & 31);
+                        const float c1 = __shfl_sync(0xffffffffu, ccr[k >> 5], (k & 31) + 1);
+                        const float e0 = ex2_approx(fmaf(__uint_as_float(v[k]), a, nb));
+                        const float e1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), a, nb));
+                        packed[k / 2] = pack2<BF16>(e0 * (rcg + c0), e1 * (rcg + c1));
+                    }
                 }
                 if (nvalid < 128) {  // ragged last tile (rare): columns that do not exist contribute nothing
 #pragma unroll
@@ -477,9 +503,11 @@ bool pair_backward_supported(int64_t dpad) { return dpad <= PAIR_DCH; }
 int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
-                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask) {
+                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask, const int32_t* pos_lo,
+                          const float* pos_cnt, const float* lam2) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % P_BK == 0 && dpad <= PAIR_DCH, "pair backward needs a padded feature dim <= 768");
+    CLIBD_REQUIRE(lam2 == nullptr || (pos_lo != nullptr && pos_cnt != nullptr), "lam2 needs the positive ranges");
     static bool attr_set = false;
     if (!attr_set) {
         CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
@@ -507,7 +535,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     auto kern = fmt_bf16 ? loss_bwd_pair_kernel<true> : loss_bwd_pair_kernel<false>;
     kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
                                                piece_w, tiles_per_split, scale, idesc_s, idesc_g, rowcoef, colcoef,
-                                               gscale, weight, accumulate, dxh, self_mask);
+                                               gscale, weight, accumulate, dxh, self_mask, pos_lo, pos_cnt,
+                                               lam2);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

@@ -29,7 +29,13 @@ struct LossPlan {
     int64_t row_parts = 0;   // forward: number of row-sum partials per row
     int64_t col_parts = 0;   // forward: number of col-sum partials per column
     size_t off_rep = 0, off_cnt = 0, off_gscale = 0;
-    size_t off_xh[3] = {0, 0, 0}, off_xhT[3] = {0, 0, 0}, off_Q[3] = {0, 0, 0}, off_dxh[3] = {0, 0, 0};
+    // xh: 16-bit unit rows in INPUT order (row operand); xhS / xhT: the same rows in CLASS-SORTED order and their
+    // transpose (column operands: every row's positives are then one contiguous column range)
+    size_t off_xh[3] = {0, 0, 0}, off_xhS[3] = {0, 0, 0}, off_xhT[3] = {0, 0, 0}, off_Q[3] = {0, 0, 0}, off_dxh[3] = {0, 0, 0};
+    // class_lo[i]: first sorted position of the class of row i; ccS: the current sweep's column coefficients in
+    // sorted order; posrow2[2p+dir][n]: xhat_i . Q_partner[rep_i] per pair and direction; lam2[2p+dir][n]: the part
+    // of the "- 2 T_ij" target term that the tensor-core epilogue subtracts (see loss_bwd_pair.cu)
+    size_t off_cstart = 0, off_class_lo = 0, off_ccS = 0, off_posrow2 = 0, off_lam2 = 0;
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
     // label hash table (own/min/count per slot), rows sorted by class (keys, indices), sort input and CUB scratch
@@ -63,21 +69,33 @@ int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStre
 // Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r
 int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
                       const float* cnt, int64_t N, int64_t d, float* Q, cudaStream_t s);
-// 16-bit normalised operand copies: xh [N,dpad] and its transpose xhT [dpad,npad] (zero padded)
+// 16-bit normalised operand copies: xh [N,dpad] in input order; with perm != null also xhS [N,dpad] whose row k is
+// input row perm[k], and the transpose xhT [dpad,npad] (zero padded) follows that order (perm == null: input order)
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
-                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s);
+                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s,
+                         const int32_t* perm = nullptr, void* xhS = nullptr);
+// class_lo[i] = first position of the class of row i in the class-sorted order (skey = sorted representatives)
+int launch_class_ranges(const int32_t* skey, const int32_t* rep, int64_t N, int32_t* cstart, int32_t* class_lo,
+                        cudaStream_t s);
+// Per backward sweep: ccS[k] = colcoef[sidx[k]] (column coefficients in sorted order; sidx == null: copy) and, when
+// lam2 != null, lam2[i] = 2 min(1, 0.5 exp(s posrow_i / cnt_i - s) (rowcoef_i + colcoef_i)) for the local rows
+int launch_sweep_prep(const float* rowcoef, const float* colcoef, const int32_t* sidx, const float* cnt,
+                      const float* posrow, int64_t N, int64_t row0, int64_t n, float scale, float* ccS, float* lam2,
+                      cudaStream_t s);
 // posrow[i] = xhat_a[row0+i] . Qb[rep[row0+i]]
 int launch_pos_rows(const void* xa, int dtype, const float* inv_a, const float* Qb, const int32_t* rep, int64_t d,
                     int64_t row0, int64_t n, float* posrow, cudaStream_t s);
 // out[k] = sum_{p < parts} part[p*stride + k] for k < len (fixed order)
-int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s);
+// (scatter != null: out[scatter[k]] instead of out[k])
+int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s,
+                        const int32_t* scatter = nullptr);
 // out[0] = mul * sum_k in[k] in double, fixed order
 int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s);
 // loss + backward coefficients u = cnt/rowsum, v = cnt/colsum
 int launch_loss_finish(int64_t N, float scale, const float w[3], const float* cnt, const float* rowsum,
                        const float* colsum, const double* pos, float* u, float* v, double* red, float* loss_out,
                        cudaStream_t s);
-// dx = grad_scale * normalize_bwd( (scale/N) * (sum_splits dxh - 2 * sum_partners w_p Q_partner[rep]) );
+// dx = grad_scale * normalize_bwd( (scale/N) * (sum_splits dxh - sum_partners w_p (2 - lam2_p,i) Q_partner[rep]) );
 // dots[i] = xhat_i . dxhat_i for unit grad
 struct NormBwdArgs {
     const void* x;
@@ -88,6 +106,7 @@ struct NormBwdArgs {
     int jsplit;
     const float* Qp[2];     // partner class sums (may be null)
     float wp[2];            // their pair weights
+    const float* lam2[2] = {nullptr, nullptr};  // [n] part of the target term already subtracted by the sweep (null: 0)
     int64_t N, d, row0, n;
     float scale, grad_scale;
     const float* grad_scale_dev;  // optional device scalar multiplied into grad_scale (may be null)
@@ -121,7 +140,10 @@ bool pair_backward_supported(int64_t dpad);
 int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y, int64_t N, int64_t npad, int64_t d,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
-                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask = 0);
+                          int fmt_bf16, float* dxh, cudaStream_t s, int self_mask = 0,
+                          const int32_t* pos_lo = nullptr, const float* pos_cnt = nullptr, const float* lam2 = nullptr);
+// pos_lo / pos_cnt [N] (by global row), lam2 [n] (by local row): columns [pos_lo, pos_lo + pos_cnt) of row i are its
+// positives (T_ij = 1) and the epilogue subtracts lam2_i from G~ there before the 16-bit rounding
 // self_mask = 1 (all four launchers above): the operands are the SAME feature set and the entries whose global row
 // equals their column are excluded from the sums (SimCLR info-NCE, bioscanclip/util/simclr.py:76-79)
 int tc_num_sms();

@@ -210,27 +210,31 @@ __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restri
 }
 
 // 64 x 64 tile: xh[row][col] = cvt(x * inv) (zero for col >= d), xhT[col][row] (zero for row >= N); 16-byte
-// global accesses on both outputs (and on the input when rows are 16-byte aligned)
+// global accesses on both outputs (and on the input when rows are 16-byte aligned).  With perm the tile walks the
+// rows in permuted order: position k holds input row perm[k]; xh stays in input order, xhS / xhT follow perm.
 template <typename T, bool VEC>
 __global__ void make_operands_kernel(const T* __restrict__ x, const float* __restrict__ inv, int64_t N, int64_t d,
                                      int64_t dpad, int64_t npad, int fmt_bf16, uint16_t* __restrict__ xh,
-                                     uint16_t* __restrict__ xhT) {
+                                     uint16_t* __restrict__ xhT, const int32_t* __restrict__ perm,
+                                     uint16_t* __restrict__ xhS) {
     __shared__ __align__(16) uint16_t tile[64][72];
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 64, r0 = static_cast<int64_t>(blockIdx.y) * 64;
     for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) {
         const int rr = idx >> 3, ch = idx & 7;
         const int64_t row = r0 + rr, col = c0 + ch * 8;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int64_t src = row;
         if (row < N) {
-            const float iv = inv ? inv[row] : 1.f;
+            if (perm) src = perm[row];
+            const float iv = inv ? inv[src] : 1.f;
             if (VEC && col + 8 <= d) {
-                load8(x + row * d + col, v);
+                load8(x + src * d + col, v);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] *= iv;
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (col + k < d) v[k] = load_as_float(x + row * d, col + k) * iv;
+                    if (col + k < d) v[k] = load_as_float(x + src * d, col + k) * iv;
             }
         }
         uint4 pk;
@@ -238,7 +242,10 @@ __global__ void make_operands_kernel(const T* __restrict__ x, const float* __res
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = pack2_operand16(v[2 * k], v[2 * k + 1], fmt_bf16);
         *reinterpret_cast<uint4*>(&tile[rr][ch * 8]) = pk;
-        if (row < N && col < dpad) *reinterpret_cast<uint4*>(xh + row * dpad + col) = pk;
+        if (row < N && col < dpad) {
+            *reinterpret_cast<uint4*>(xh + src * dpad + col) = pk;
+            if (xhS) *reinterpret_cast<uint4*>(xhS + row * dpad + col) = pk;
+        }
     }
     __syncthreads();
     if (xhT != nullptr) {
@@ -274,12 +281,43 @@ __global__ void pos_rows_kernel(const T* __restrict__ xa, const float* __restric
 }
 
 __global__ void reduce_parts_kernel(const float* __restrict__ part, int64_t parts, int64_t stride, int64_t len,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, const int32_t* __restrict__ scatter) {
     int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k >= len) return;
     float acc = 0.f;
     for (int64_t p = 0; p < parts; ++p) acc += part[p * stride + k];
-    out[k] = acc;
+    out[scatter ? scatter[k] : k] = acc;
+}
+
+// class_start[r] = first sorted position of the class whose representative is r
+__global__ void class_start_kernel(const int32_t* __restrict__ skey, int64_t N, int32_t* __restrict__ cstart) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int32_t r = skey[k];
+    if (k == 0 || skey[k - 1] != r) cstart[r] = static_cast<int32_t>(k);
+}
+
+__global__ void class_lo_kernel(const int32_t* __restrict__ rep, const int32_t* __restrict__ cstart, int64_t N,
+                                int32_t* __restrict__ class_lo) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < N) class_lo[i] = cstart[rep[i]];
+}
+
+// ccS[k] = colcoef[sidx[k]]; lam2[i] = 2 min(1, 0.5 e_i (rowcoef_i + colcoef_i)), e_i = exp(s (posrow_i / cnt_i - 1)):
+// the value G~ takes on a row's positives when they all sit at the row's mean positive similarity.  ANY lam2 in
+// [0, 2] is algebraically exact (the epilogue subtracts lam2 on the positives, the fp32 class-sum term the
+// remaining 2 - lam2); this choice makes the 16-bit rounded operand G~ - lam2 small exactly when G~ -> 2 T.
+__global__ void sweep_prep_kernel(const float* __restrict__ rowcoef, const float* __restrict__ colcoef,
+                                  const int32_t* __restrict__ sidx, const float* __restrict__ cnt,
+                                  const float* __restrict__ posrow, int64_t N, int64_t row0, int64_t n, float scale,
+                                  float* __restrict__ ccS, float* __restrict__ lam2) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k < N) ccS[k] = colcoef[sidx ? sidx[k] : k];
+    if (lam2 != nullptr && k < n) {
+        const int64_t gi = row0 + k;
+        const float e = expf(scale * (posrow[k] / cnt[gi] - 1.f));
+        lam2[k] = 2.f * fminf(1.f, 0.5f * e * (rowcoef[gi] + colcoef[gi]));
+    }
 }
 
 constexpr int kRedBlocks = 256;
@@ -366,6 +404,9 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
     const float k1 = a.scale / static_cast<float>(a.N);
     const float gsc = a.grad_scale * (a.grad_scale_dev ? a.grad_scale_dev[0] : 1.f);
     T* dxr = a.dx ? reinterpret_cast<T*>(a.dx) + i * a.d : nullptr;
+    // effective partner weights: the sweep already subtracted lam2 of the 2 on this row's positives
+    const float wpe[2] = {a.wp[0] * (a.lam2[0] ? 1.f - 0.5f * a.lam2[0][i] : 1.f),
+                          a.wp[1] * (a.lam2[1] ? 1.f - 0.5f * a.lam2[1][i] : 1.f)};
     if constexpr (VEC) {
         auto dxhat8 = [&](int64_t c, float (&g)[8]) {
 #pragma unroll
@@ -383,7 +424,7 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
                     float t[8];
                     load8(a.Qp[pz] + rp * a.d + c, t);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) q[k] = fmaf(a.wp[pz], t[k], q[k]);
+                    for (int k = 0; k < 8; ++k) q[k] = fmaf(wpe[pz], t[k], q[k]);
                 }
             }
 #pragma unroll
@@ -444,8 +485,8 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
             float g = 0.f;
             for (int s = 0; s < a.jsplit; ++s) g += a.dxh[(static_cast<int64_t>(s) * a.n + i) * a.d + c];
             float t = 0.f;
-            if (a.Qp[0]) t = fmaf(a.wp[0], a.Qp[0][rp * a.d + c], t);
-            if (a.Qp[1]) t = fmaf(a.wp[1], a.Qp[1][rp * a.d + c], t);
+            if (a.Qp[0]) t = fmaf(wpe[0], a.Qp[0][rp * a.d + c], t);
+            if (a.Qp[1]) t = fmaf(wpe[1], a.Qp[1][rp * a.d + c], t);
             return k1 * (g - 2.f * t);
         };
         float part = 0.f;
@@ -538,7 +579,8 @@ int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int
 }
 
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
-                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s) {
+                         int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s, const int32_t* perm,
+                         void* xhS) {
     const int64_t rows = npad > N ? npad : N;
     dim3 grid(static_cast<unsigned>(ceil_div(dpad, 64)), static_cast<unsigned>(ceil_div(rows, 64)));
     const bool vec = rows_vec8_ok<void>(x, d);
@@ -546,11 +588,13 @@ int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_
         if (vec)
             make_operands_kernel<T, true><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, N, d, dpad, npad,
                                                                     fmt_bf16, static_cast<uint16_t*>(xh),
-                                                                    static_cast<uint16_t*>(xhT));
+                                                                    static_cast<uint16_t*>(xhT), perm,
+                                                                    static_cast<uint16_t*>(xhS));
         else
             make_operands_kernel<T, false><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, N, d, dpad, npad,
                                                                      fmt_bf16, static_cast<uint16_t*>(xh),
-                                                                     static_cast<uint16_t*>(xhT));
+                                                                     static_cast<uint16_t*>(xhT), perm,
+                                                                     static_cast<uint16_t*>(xhS));
     });
     CLIBD_KERNEL_CHECK();
     return 0;
@@ -565,9 +609,30 @@ int launch_pos_rows(const void* xa, int dtype, const float* inv_a, const float* 
     return 0;
 }
 
-int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s) {
+int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s,
+                        const int32_t* scatter) {
     if (len == 0) return 0;
-    reduce_parts_kernel<<<ceil_div(len, kThreads), kThreads, 0, s>>>(part, parts, stride, len, out);
+    reduce_parts_kernel<<<ceil_div(len, kThreads), kThreads, 0, s>>>(part, parts, stride, len, out, scatter);
+    CLIBD_KERNEL_CHECK();
+    return 0;
+}
+
+int launch_class_ranges(const int32_t* skey, const int32_t* rep, int64_t N, int32_t* cstart, int32_t* class_lo,
+                        cudaStream_t s) {
+    if (N == 0) return 0;
+    class_start_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(skey, N, cstart);
+    CLIBD_KERNEL_CHECK();
+    class_lo_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(rep, cstart, N, class_lo);
+    CLIBD_KERNEL_CHECK();
+    return 0;
+}
+
+int launch_sweep_prep(const float* rowcoef, const float* colcoef, const int32_t* sidx, const float* cnt,
+                      const float* posrow, int64_t N, int64_t row0, int64_t n, float scale, float* ccS, float* lam2,
+                      cudaStream_t s) {
+    if (N == 0) return 0;
+    sweep_prep_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(rowcoef, colcoef, sidx, cnt, posrow, N, row0, n, scale,
+                                                               ccS, lam2);
     CLIBD_KERNEL_CHECK();
     return 0;
 }
