@@ -210,12 +210,45 @@ def run_ours(args):
         loss.backward()
         return loss
 
+    # End-to-end step: what a training loop with a prefetching loader does.  Every step copies ITS inputs from
+    # pinned host memory into one of two device slots on a copy stream (issued one step ahead, so the copy of
+    # step k+1 overlaps the kernels of step k) and reads the PREVIOUS step's loss on the host (the last one is
+    # read by the synchronize that closes the timed region): K copies and K loss reads per K timed steps.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{"feats": [torch.empty_like(r) for r in resident], "labels": torch.empty_like(resident_labels),
+              "ready": None, "free": None} for _ in range(2)]
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [None, None]
+    pipe = {"k": 0, "last": None}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            if slot["free"] is not None:
+                copy_stream.wait_event(slot["free"])  # the step that used this slot has finished reading it
+            for dst, src in zip(slot["feats"], host):
+                dst.copy_(src, non_blocking=True)
+            slot["labels"].copy_(host_labels, non_blocking=True)
+            slot["ready"] = copy_stream.record_event()
+
     def step_e2e():
-        leaves = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host]
-        labels = host_labels.to(dev, non_blocking=True)
-        loss = module(leaves[0], leaves[1], leaves[2], labels, scale)
+        k = pipe["k"]
+        cur, nxt = slots[k % 2], slots[(k + 1) % 2]
+        if cur["ready"] is None:
+            issue_copy(cur)  # very first call: nothing was prefetched yet
+        stream = torch.cuda.current_stream(dev)
+        stream.wait_event(cur["ready"])
+        issue_copy(nxt)
+        leaves = [f.detach().requires_grad_(True) for f in cur["feats"]]
+        loss = module(leaves[0], leaves[1], leaves[2], cur["labels"], scale)
         loss.backward()
-        return float(loss)  # device -> host read of the step's result
+        cur["free"] = stream.record_event()
+        loss_host[k % 2].copy_(loss.detach(), non_blocking=True)  # device -> host read of the step's result
+        loss_evt[k % 2] = stream.record_event()
+        if loss_evt[(k + 1) % 2] is not None:
+            loss_evt[(k + 1) % 2].synchronize()
+            pipe["last"] = float(loss_host[(k + 1) % 2])
+        pipe["k"] = k + 1
+        return pipe["last"]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -355,9 +388,13 @@ def bench_knn(torch, dist, R, lib, dev, rank, world, timed, peak_tf):
     del queries, keys
 
     def step_e2e():
+        # host-resident queries and keys: the key set is copied block-wise on a copy stream while the previous
+        # block is normalised and screened (what knn_search / make_prediction do for host inputs)
+        if world == 1:
+            _, idx = R.knn_search(host_q, host_k, k, mode="fp16", device=dev)
+            return idx.cpu()
         qd = R.normalize_rows(host_q, dev)
-        kd = R.normalize_rows(host_k, dev)
-        s64, idx, _ = R.search_normalized(qd, kd, k, key_offset=lo, mode="fp16")
+        s64, idx = R._search_host_keys_pipelined(qd, host_k, 0, host_k.shape[0], k, "fp16", dev, index_base=lo)
         if world > 1:
             all_s = torch.empty((world,) + tuple(s64.shape), dtype=torch.float64, device=dev)
             all_i = torch.empty((world,) + tuple(idx.shape), dtype=torch.int64, device=dev)

@@ -231,7 +231,7 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
         if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
     for (int m = 0; m < 3; ++m) {
         if (!used[m]) continue;
-        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], ls.skey, ls.sidx, cnt, N, d, at<float>(scratch, plan.off_Q[m]), stream)))
+        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], ls.skey, ls.sidx, cnt, N, d, row0, n, at<float>(scratch, plan.off_Q[m]), stream)))
             return rc;
         if (tc) {
             // row operand in input order, column operands (xhS, xhT) in class-sorted order

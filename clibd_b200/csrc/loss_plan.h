@@ -66,9 +66,10 @@ int launch_label_stats(const int64_t* labels, int64_t N, int32_t* rep, float* cn
                        cudaStream_t s);
 // gscale[0] = power-of-two scale applied to 16-bit G operands (1 for bf16), gscale[1] = 1/gscale[0]
 int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStream_t s);
-// Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r
+// Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r whose class has a member
+// among the local rows [row0, row0 + n) (the only class sums a rank reads)
 int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
-                      const float* cnt, int64_t N, int64_t d, float* Q, cudaStream_t s);
+                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s);
 // 16-bit normalised operand copies: xh [N,dpad] in input order; with perm != null also xhS [N,dpad] whose row k is
 // input row perm[k], and the transpose xhT [dpad,npad] (zero padded) follows that order (perm == null: input order)
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,

@@ -176,13 +176,22 @@ __global__ void gscale_kernel(const float* __restrict__ cnt, int64_t N, int path
 template <typename T, bool VEC>
 __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restrict__ inv,
                                   const int32_t* __restrict__ skey, const int32_t* __restrict__ sidx,
-                                  const float* __restrict__ cnt, int64_t N, int64_t d, float* __restrict__ Q) {
+                                  const float* __restrict__ cnt, int64_t N, int64_t d, int64_t row0, int64_t n,
+                                  float* __restrict__ Q) {
     const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= N) return;
     const int32_t r = skey[p];
     if (p > 0 && skey[p - 1] == r) return;  // not the head of its segment
     const int members = static_cast<int>(cnt[r]);
+    if (n < N) {  // row-sharded: only classes with a member among the local rows are ever read on this rank
+        bool need = false;
+        for (int m = lane; m < members; m += 32) {
+            const int64_t j = sidx[p + m];
+            need |= (j >= row0 && j < row0 + n);
+        }
+        if (!__any_sync(0xffffffffu, need)) return;
+    }
     float* qr = Q + static_cast<int64_t>(r) * d;
     if constexpr (VEC) {
         for (int64_t c = lane * 8; c < d; c += 256) {
@@ -564,15 +573,15 @@ int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStre
 }
 
 int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
-                      const float* cnt, int64_t N, int64_t d, float* Q, cudaStream_t s) {
+                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s) {
     if (N == 0) return 0;
     const int64_t blocks = ceil_div(N * 32, kThreads);
     const bool vec = rows_vec8_ok<void>(x, d) && rows_vec8_ok<void>(Q, d);
     DISPATCH_DTYPE(dtype, {
         if (vec && (sizeof(T) == 2 || d % 8 == 0))
-            class_sums_kernel<T, true><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, Q);
+            class_sums_kernel<T, true><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q);
         else
-            class_sums_kernel<T, false><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, Q);
+            class_sums_kernel<T, false><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q);
     });
     CLIBD_KERNEL_CHECK();
     return 0;

@@ -111,6 +111,75 @@ def merge_topk(sims64_parts: torch.Tensor, idx_parts: torch.Tensor):
     return out64, out32, oidx
 
 
+_PIPELINE_MIN_KEYS = 1 << 17   # host-resident key sets at least this large are copied and searched block-wise
+_PIPELINE_BLOCKS = 4
+
+
+def _as_host_tensor(x):
+    """x as a CPU float tensor without copying, or None when it already lives on a device."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return None
+        t = x.detach()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if t.dtype not in (torch.float32, torch.float64):
+        return None
+    return t.contiguous()
+
+
+def _search_block(q32, k32, k, key_offset, mode):
+    """top-k of one normalised key block, padded with empty slots to k columns."""
+    device = q32.device
+    kk = min(k, k32.shape[0])
+    s64, idx, _ = search_normalized(q32, k32, kk, key_offset=key_offset, mode=mode)
+    if kk < k:
+        pad_s = torch.full((q32.shape[0], k - kk), -torch.finfo(torch.float64).max, dtype=torch.float64, device=device)
+        pad_i = torch.full((q32.shape[0], k - kk), -1, dtype=torch.int64, device=device)
+        s64, idx = torch.cat([s64, pad_s], 1), torch.cat([idx, pad_i], 1)
+    return s64, idx
+
+
+def _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device, blocks=_PIPELINE_BLOCKS, index_base=0):
+    """Keys [lo, hi) live in host memory: copy them block by block on a copy stream into two staging buffers
+    while the previous block is normalised and searched, then merge the per-block lists by (-sim, index) --
+    the same order the shard merge uses, so the result equals the one-shot search bit for bit.  Hides the
+    host->device copy of the key set (3 GB for 1M x 768 float32) behind the tensor-core screen.
+    Returned indices are index_base + the row number inside host_keys."""
+    blocks = max(1, min(blocks, hi - lo))
+    bounds = [lo + (hi - lo) * b // blocks for b in range(blocks + 1)]
+    longest = max(bounds[b + 1] - bounds[b] for b in range(blocks))
+    cur = torch.cuda.current_stream(device)
+    copy_stream = torch.cuda.Stream(device=device)
+    stage = [torch.empty((longest, host_keys.shape[1]), dtype=host_keys.dtype, device=device) for _ in range(2)]
+    ready, free = [None, None], [None, None]
+    copy_stream.wait_stream(cur)  # the staging buffers exist before the first copy lands in them
+
+    def issue(b):
+        sl = b % 2
+        with torch.cuda.stream(copy_stream):
+            if free[sl] is not None:
+                copy_stream.wait_event(free[sl])
+            stage[sl][:bounds[b + 1] - bounds[b]].copy_(host_keys[bounds[b]:bounds[b + 1]], non_blocking=True)
+            ready[sl] = copy_stream.record_event()
+
+    issue(0)
+    parts_s, parts_i = [], []
+    for b in range(blocks):
+        if b + 1 < blocks:
+            issue(b + 1)
+        sl = b % 2
+        cur.wait_event(ready[sl])
+        k32 = normalize_rows(stage[sl][:bounds[b + 1] - bounds[b]], device)
+        free[sl] = cur.record_event()  # the staging buffer has been read
+        s64, idx = _search_block(q32, k32, k, index_base + bounds[b], mode)
+        parts_s.append(s64)
+        parts_i.append(idx)
+        del k32
+    s64, _, idx = merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    return s64, idx
+
+
 def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=None, process_group=None,
                shard_keys: bool = False):
     """normalise + search (+ shard merge).  Returns (similarities float32 [Q,k], indices int64 [Q,k])
@@ -129,13 +198,11 @@ def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=N
     per = (nk + world - 1) // world
     lo, hi = min(nk, rank * per), min(nk, (rank + 1) * per)
     if hi > lo:
-        k32 = normalize_rows(keys_feature[lo:hi], device)
-        kk = min(k, hi - lo)
-        s64, idx, _ = search_normalized(q32, k32, kk, key_offset=lo, mode=mode)
-        if kk < k:  # pad a short shard with empty slots
-            pad_s = torch.full((q32.shape[0], k - kk), -torch.finfo(torch.float64).max, dtype=torch.float64, device=device)
-            pad_i = torch.full((q32.shape[0], k - kk), -1, dtype=torch.int64, device=device)
-            s64, idx = torch.cat([s64, pad_s], 1), torch.cat([idx, pad_i], 1)
+        host_keys = _as_host_tensor(keys_feature)
+        if host_keys is not None and hi - lo >= _PIPELINE_MIN_KEYS:
+            s64, idx = _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device)
+        else:
+            s64, idx = _search_block(q32, normalize_rows(keys_feature[lo:hi], device), k, lo, mode)
     else:
         s64 = torch.full((q32.shape[0], k), -torch.finfo(torch.float64).max, dtype=torch.float64, device=device)
         idx = torch.full((q32.shape[0], k), -1, dtype=torch.int64, device=device)

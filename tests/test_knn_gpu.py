@@ -113,6 +113,30 @@ def test_shard_merge_equals_unsharded():
     assert torch.equal(m32, s_all.float())
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_keys_pipelined_search_equals_one_shot(monkeypatch, pinned):
+    """knn_search on HOST-resident keys copies and searches them block-wise (copy stream + two staging buffers)
+    and merges the block lists: indices and similarities must equal the one-shot device search bit for bit,
+    including duplicates that straddle block boundaries and a block shorter than k."""
+    from clibd_b200 import retrieval as R
+    dev = torch.device("cuda:0")
+    q, keys, _, _ = _taxonomy_data(300, 4003, 128, seed=9, dup=300)
+    keys[1000:1003] = keys[5:8]          # exact duplicates in different blocks
+    q32, k32 = R.normalize_rows(q, dev), R.normalize_rows(keys, dev)
+    s_all, i_all, _ = R.search_normalized(q32, k32, 5, mode="fp16")
+    monkeypatch.setattr(R, "_PIPELINE_MIN_KEYS", 1)
+    host = torch.from_numpy(keys)
+    if pinned:
+        host = host.pin_memory()
+    s32, idx = R.knn_search(q, host, 5, mode="fp16", device=dev)
+    assert torch.equal(idx, i_all) and torch.equal(s32, s_all.float())
+    # more blocks than k rows per block: 3 keys over 4 blocks -> blocks of 0/1 rows are padded
+    s3, i3 = R._search_host_keys_pipelined(q32, torch.from_numpy(keys[:3].copy()), 0, 3, 3, "fp16", dev, blocks=2,
+                                           index_base=10)
+    s_ref, i_ref, _ = R.search_normalized(q32, k32[:3].contiguous(), 3, key_offset=10, mode="fp16")
+    assert torch.equal(i3, i_ref) and torch.equal(s3, s_ref)
+
+
 def test_make_prediction_and_eval_entry_point_match_oracle():
     import clibd_b200 as cb
     rng = np.random.default_rng(12)

@@ -1,1 +1,3 @@
-timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -s 2>&1 | grep -E "saturated|trained regime|passed|failed|FAILED|Error|assert" | head -60
+mkdir -p gpurun_out
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r1f.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-knn > gpurun_out/launches_r1f.log 2>&1
+tail -3 gpurun_out/launches_r1f.log | cut -c1-300
