@@ -324,6 +324,9 @@ def run_ours(args):
     # pair = 2*n*N*d per ordered-sweep launch (the S recompute is NOT credited)
     roofline = roof(1, 2.0 * n * N * d, "loss_bwd_pair_kernel")
     roofline_fwd = roof(0, 2.0 * n * N * d, "loss_fwd_pair_kernel")
+    # single-GPU backward: the other side's gradient of every pair is a plain GEMM over the stored coefficient
+    # strip (2*n*N*d per pair, no S recompute); absent when the rows are sharded (two sweeps per pair instead)
+    roofline_grad = roof(4, 2.0 * n * N * d * (prof_n[1] / prof_n[4]) if prof_n[4] else 0.0, "loss_grad_gemm_kernel")
     step_frac = (18.0 * n * N * d) / (ms_step * 1e-3) / 1e12 / peak_tf
 
     out = {
@@ -331,7 +334,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "roofline_fwd": roofline_fwd, "step_tensor_frac_algorithmic": step_frac,
+        "roofline_fwd": roofline_fwd, "roofline_grad": roofline_grad, "step_tensor_frac_algorithmic": step_frac,
     }
 
     # ---------------- kNN workload

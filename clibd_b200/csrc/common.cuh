@@ -19,7 +19,7 @@ void set_error(const std::string& msg);
 // telemetry (loss_api.cu): number of kernels this library launched, and optional CUDA-event timing
 // of the tensor-core kernels on their launching stream (slots below)
 void count_launch();
-enum : int { PROF_LOSS_FWD_TC = 0, PROF_LOSS_BWD_TC = 1, PROF_KNN_SCREEN_TC = 2, PROF_KNN_RERANK = 3, PROF_SLOTS = 8 };
+enum : int { PROF_LOSS_FWD_TC = 0, PROF_LOSS_BWD_TC = 1, PROF_KNN_SCREEN_TC = 2, PROF_KNN_RERANK = 3, PROF_LOSS_GRAD_GEMM = 4, PROF_SLOTS = 8 };
 struct ProfScope {
     ProfScope(int slot, cudaStream_t s);
     ~ProfScope();

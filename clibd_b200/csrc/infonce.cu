@@ -103,7 +103,7 @@ int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64
                           float inv_temperature, int path, void* scratch, int64_t scratch_bytes, float* rowsum,
                           float* loss_out, clibd_stream_t stream) {
     CLIBD_REQUIRE(M > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
-    const LossPlan plan = make_loss_plan(M, M, d, path);
+    const LossPlan plan = make_loss_plan(M, M, d, path, /*allow_shared_s=*/false);
     int rc = check_args(z, inv_norm, dtype, M, d, inv_temperature, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(rowsum && loss_out, "null output pointer");
@@ -153,7 +153,7 @@ int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int6
                            float inv_temperature, int path, void* scratch, int64_t scratch_bytes,
                            float grad_scale, const float* grad_scale_dev, void* dz, clibd_stream_t stream) {
     CLIBD_REQUIRE(M > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
-    const LossPlan plan = make_loss_plan(M, M, d, path);
+    const LossPlan plan = make_loss_plan(M, M, d, path, /*allow_shared_s=*/false);
     int rc = check_args(z, inv_norm, dtype, M, d, inv_temperature, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(dz != nullptr, "null output pointer");

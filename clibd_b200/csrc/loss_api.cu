@@ -38,7 +38,7 @@ ProfScope::~ProfScope() {
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
+LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_shared_s) {
     LossPlan p;
     p.N = N;
     p.n = n;
@@ -100,6 +100,25 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path) {
     p.off_ccS = take(sizeof(float) * N);
     p.off_posrow2 = take(sizeof(float) * 6 * n);
     p.off_lam2 = take(sizeof(float) * 6 * n);
+    // Single-GPU tcgen05 pair path: S is computed once per pair; the row sweep stores its 16-bit coefficients
+    // transposed in a strip buffer (CLIBD_GT_STRIP_MB, default 2304 MB = the whole column range at
+    // N = 32768, and never fewer than 18944 columns) and the other side's gradient is a plain GEMM over that strip.
+    p.shared_s = allow_shared_s && tc && n == N && p.dpad <= PAIR_DCH && !std::getenv("CLIBD_BWD_TWO_SWEEPS") &&
+                 !std::getenv("CLIBD_BWD_SINGLE");
+    if (p.shared_s) {
+        const char* env = std::getenv("CLIBD_GT_STRIP_MB");
+        const double budget = (env ? std::atof(env) : 2304.0) * 1048576.0;
+        p.gt_ld = round_up(N, 64);
+        int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(p.gt_ld))) / 256 * 256;
+        if (rows < 74 * 256) rows = 74 * 256;  // at least one 256-row tile per CTA pair and feature tile
+        const int64_t all = round_up(N, 256);
+        p.strip_rows = rows < all ? rows : all;
+        p.off_gt = take(2 * static_cast<size_t>(p.strip_rows) * p.gt_ld);
+        for (int m = 0; m < 3; ++m) {
+            p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad);
+            p.off_Qw[m] = take(sizeof(float) * N * d);
+        }
+    }
     p.off_dots = take(sizeof(float) * 3 * n);
     p.off_red = take(sizeof(double) * 512);
     const int64_t H = label_hash_slots(N);
@@ -133,6 +152,102 @@ static int check_common(const void* const x[3], const float* const inv_norm[3], 
         }
     }
     return 0;
+}
+
+
+// Single-GPU backward with S computed ONCE per modality pair (plan.shared_s).  For pair p = (a, b):
+//   1. row sweep over the rows of a (loss_bwd_pair.cu): S tile -> G~ (minus lam2_i on the positives) ->
+//      dxh[a] += G~ Yhat_b, and the same 16-bit G~ stored transposed into the strip buffer;
+//   2. dxh[b] += Gt * Xhat_a as a plain GEMM (loss_grad_gemm.cu) -- no second S^T sweep;
+//   3. the fp32 target term of b's rows uses class sums of a weighted by 1 - lam2_i / 2 (the share the sweep
+//      has not subtracted), the one of a's rows the usual (2 - lam2_i) Q_b[rep_i].
+// Tensor work per pair: 2 (S) + 2 + 2 = 6 n N d flops instead of 8 for two sweeps.
+static int backward_shared_s(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                             float logit_scale, const float pair_weight[3], int path, void* scratch,
+                             const LossPlan& plan, float grad_feat_scale, const float* grad_feat_scale_dev,
+                             void* const dx[3], double* dscale_partial, cudaStream_t stream) {
+    const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
+    const int32_t* rep = at<int32_t>(scratch, plan.off_rep);
+    const float* gscale = at<float>(scratch, plan.off_gscale);
+    const float* u = at<float>(scratch, plan.off_u);
+    const float* v = at<float>(scratch, plan.off_v);
+    const float* cnt = at<float>(scratch, plan.off_cnt);
+    const int32_t* skey = at<int32_t>(scratch, plan.off_skey);
+    const int32_t* sidx = at<int32_t>(scratch, plan.off_sidx);
+    const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
+    float* ccS = at<float>(scratch, plan.off_ccS);
+    float* dots = at<float>(scratch, plan.off_dots);
+    double* red = at<double>(scratch, plan.off_red);
+    void* gt = at<void>(scratch, plan.off_gt);
+    int rc = 0;
+    int nparts[3] = {0, 0, 0};
+    const float* Qp[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    const float* lam[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    float wp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] == 0.f) continue;
+        const int a = kPairA[p], b = kPairB[p];
+        float* lam2 = at<float>(scratch, plan.off_lam2) + (2 * p) * N;
+        if ((rc = launch_sweep_prep(u + p * N, v + p * N, sidx, cnt, at<float>(scratch, plan.off_posrow2) + (2 * p) * N, N, 0,
+                                    N, logit_scale, ccS, lam2, stream)))
+            return rc;
+        float* dxh_a = at<float>(scratch, plan.off_dxh[a]);
+        float* dxh_b = at<float>(scratch, plan.off_dxh[b]);
+        int strip = 0;
+        for (int64_t c0 = 0; c0 < N; c0 += plan.strip_rows, ++strip) {
+            const int64_t c1 = c0 + plan.strip_rows < N ? c0 + plan.strip_rows : N;
+            if ((rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]),
+                                            at<void>(scratch, plan.off_xhT[b]), N, plan.npad, d, plan.dpad, 0, N, logit_scale,
+                                            u + p * N, ccS, gscale, pair_weight[p], nparts[a] > 0 || strip > 0, plan.jsplit,
+                                            fmt_bf16, dxh_a, stream, /*self_mask=*/0, class_lo, cnt, lam2, c0, c1, gt,
+                                            plan.gt_ld)))
+                return rc;
+            if ((rc = tc_grad_from_strip(gt, plan.gt_ld, c1 - c0, c0, at<void>(scratch, plan.off_xhTo[a]), N, plan.npad, d,
+                                         plan.dpad, sidx, gscale, pair_weight[p], nparts[b] > 0, plan.jsplit, fmt_bf16, dxh_b,
+                                         N, tc_num_sms(), stream)))
+                return rc;
+        }
+        // target terms: rows of a see Q_b with their own lam2; rows of b see the lam2-weighted class sums of a
+        float* Qw = at<float>(scratch, plan.off_Qw[p]);
+        if ((rc = launch_class_sums(x[a], dtype, inv_norm[a], skey, sidx, cnt, N, d, 0, N, Qw, stream, lam2))) return rc;
+        Qp[a][nparts[a]] = at<float>(scratch, plan.off_Q[b]);
+        lam[a][nparts[a]] = lam2;
+        wp[a][nparts[a]] = pair_weight[p];
+        ++nparts[a];
+        Qp[b][nparts[b]] = Qw;
+        lam[b][nparts[b]] = nullptr;
+        wp[b][nparts[b]] = pair_weight[p];
+        ++nparts[b];
+    }
+    int n_mod_used = 0;
+    for (int m = 0; m < 3; ++m) {
+        if (nparts[m] == 0) continue;
+        NormBwdArgs a;
+        a.x = x[m];
+        a.dtype = dtype;
+        a.inv_norm = inv_norm[m];
+        a.rep = rep;
+        a.dxh = at<float>(scratch, plan.off_dxh[m]);
+        a.jsplit = plan.jsplit;
+        for (int k = 0; k < 2; ++k) {
+            a.Qp[k] = Qp[m][k];
+            a.wp[k] = wp[m][k];
+            a.lam2[k] = lam[m][k];
+        }
+        a.N = N;
+        a.d = d;
+        a.row0 = 0;
+        a.n = N;
+        a.scale = logit_scale;
+        a.grad_scale = grad_feat_scale;
+        a.grad_scale_dev = grad_feat_scale_dev;
+        a.dx = dx ? dx[m] : nullptr;
+        a.dots = dots + n_mod_used * N;
+        if ((rc = launch_normalize_bwd(a, stream))) return rc;
+        ++n_mod_used;
+    }
+    return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * N, 0.5 / static_cast<double>(logit_scale), red,
+                                dscale_partial, stream);
 }
 
 }  // namespace clibd
@@ -239,6 +354,11 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
                                            at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream,
                                            ls.sidx, at<void>(scratch, plan.off_xhS[m]))))
                 return rc;
+            if (plan.shared_s) {  // transposed operand in input order (K operand of the stored-coefficient GEMM)
+                if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16, nullptr,
+                                               at<void>(scratch, plan.off_xhTo[m]), stream)))
+                    return rc;
+            }
         }
     }
     float* rowpart = at<float>(scratch, plan.off_rowpart);
@@ -297,6 +417,9 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(dscale_partial != nullptr, "null dscale_partial");
+    if (plan.shared_s)
+        return backward_shared_s(x, dtype, inv_norm, N, d, logit_scale, pair_weight, path, scratch, plan, grad_feat_scale,
+                                 grad_feat_scale_dev, dx, dscale_partial, stream);
     const bool tc = path != PATH_SIMT_F32;
     const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
     const int32_t* rep = at<int32_t>(scratch, plan.off_rep);

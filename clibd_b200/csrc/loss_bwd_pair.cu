@@ -97,7 +97,8 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      uint32_t idesc_s, uint32_t idesc_g, const float* __restrict__ rowcoef,
                      const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
                      float* __restrict__ dxh, int self_mask, const int32_t* __restrict__ pos_lo,
-                     const float* __restrict__ pos_cnt, const float* __restrict__ lam2) {
+                     const float* __restrict__ pos_cnt, const float* __restrict__ lam2, int64_t jt_lo, int64_t jt_hi,
+                     uint16_t* __restrict__ gt, int64_t gt_ld) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -126,9 +127,9 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const bool leader = rank == 0;
     const int64_t mt = blockIdx.x >> 1;
     const int64_t split = blockIdx.z;
-    const int64_t num_jt = (N + PAIR_BJ - 1) / PAIR_BJ;
-    const int64_t jt0 = split * tiles_per_split;
-    const int64_t jt1 = (jt0 + tiles_per_split < num_jt) ? (jt0 + tiles_per_split) : num_jt;
+    // this launch sweeps the column tiles [jt_lo, jt_hi) (a strip of the columns, or all of them)
+    const int64_t jt0 = jt_lo + split * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < jt_hi) ? (jt0 + tiles_per_split) : jt_hi;
     const int half_w = piece_w >> 1;  // accumulator columns per piece per CTA
 
     if (threadIdx.x == 0) {
@@ -408,6 +409,16 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(g_full_l);
                 TLAP(12);
+                if (gt != nullptr && lrow < n) {
+                    // the same 16-bit coefficients, transposed, for the other side's gradient GEMM
+                    // (loss_grad_gemm.cu): Gt[column - strip start][row]; a warp writes 32 consecutive rows
+                    uint16_t* gp = gt + ((t - jt_lo) * PAIR_BJ + h * 128) * gt_ld + (row0 + lrow);
+#pragma unroll
+                    for (int p = 0; p < 64; ++p) {
+                        if (2 * p < nvalid) gp[(2 * p) * gt_ld] = static_cast<uint16_t>(packed[p] & 0xFFFFu);
+                        if (2 * p + 1 < nvalid) gp[(2 * p + 1) * gt_ld] = static_cast<uint16_t>(packed[p] >> 16);
+                    }
+                }
 #pragma unroll
                 for (int m = 0; m < 4; ++m) ccr[m] = ccn[m];
             }
@@ -504,7 +515,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
                           int fmt_bf16, float* dxh, cudaStream_t s, int self_mask, const int32_t* pos_lo,
-                          const float* pos_cnt, const float* lam2) {
+                          const float* pos_cnt, const float* lam2, int64_t col_begin, int64_t col_end, void* gt,
+                          int64_t gt_ld) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % P_BK == 0 && dpad <= PAIR_DCH, "pair backward needs a padded feature dim <= 768");
     CLIBD_REQUIRE(lam2 == nullptr || (pos_lo != nullptr && pos_cnt != nullptr), "lam2 needs the positive ranges");
@@ -526,7 +538,10 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_yt, xhT_y, dpad, npad, npad, P_BK, piece_w / 2, fmt_bf16);
     if (rc) return rc;
-    const int64_t num_jt = ceil_div(N, PAIR_BJ);
+    if (col_end < 0 || col_end > N) col_end = N;
+    CLIBD_REQUIRE(col_begin >= 0 && col_begin % PAIR_BJ == 0 && col_begin < col_end, "bad column strip");
+    const int64_t jt_lo = col_begin / PAIR_BJ, jt_hi = ceil_div(col_end, PAIR_BJ);
+    const int64_t num_jt = jt_hi - jt_lo;
     const int64_t tiles_per_split = ceil_div(num_jt, jsplit);
     const uint32_t idesc_s = make_idesc_f16(PAIR_BM, PAIR_BJ, fmt_bf16 ? 1u : 0u);
     const uint32_t idesc_g = make_idesc_f16(PAIR_BM, piece_w, fmt_bf16 ? 1u : 0u);
@@ -536,7 +551,7 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
                                                piece_w, tiles_per_split, scale, idesc_s, idesc_g, rowcoef, colcoef,
                                                gscale, weight, accumulate, dxh, self_mask, pos_lo, pos_cnt,
-                                               lam2);
+                                               lam2, jt_lo, jt_hi, static_cast<uint16_t*>(gt), gt_ld);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

@@ -36,6 +36,11 @@ struct LossPlan {
     // sorted order; posrow2[2p+dir][n]: xhat_i . Q_partner[rep_i] per pair and direction; lam2[2p+dir][n]: the part
     // of the "- 2 T_ij" target term that the tensor-core epilogue subtracts (see loss_bwd_pair.cu)
     size_t off_cstart = 0, off_class_lo = 0, off_ccS = 0, off_posrow2 = 0, off_lam2 = 0;
+    // single-GPU backward with S computed once per pair (loss_api.cu: backward_shared_s): xhTo = transposed operand
+    // in INPUT order, Qw = class sums weighted by 1 - lam2/2 (one per pair), gt = strip of transposed coefficients
+    bool shared_s = false;
+    int64_t strip_rows = 0, gt_ld = 0;
+    size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0;
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
     // label hash table (own/min/count per slot), rows sorted by class (keys, indices), sort input and CUB scratch
@@ -44,7 +49,7 @@ struct LossPlan {
     size_t total = 0;
 };
 
-LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path);
+LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path, bool allow_shared_s = true);
 
 template <typename T>
 inline T* at(void* base, size_t off) {
@@ -69,7 +74,10 @@ int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStre
 // Q[r,:] = sum over rows j with rep[j]==r of xhat_j (fp32), for every representative r whose class has a member
 // among the local rows [row0, row0 + n) (the only class sums a rank reads)
 int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
-                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s);
+                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s,
+                      const float* lam2 = nullptr);
+// (lam2 != null, indexed by row: member j enters with weight 1 - lam2[j] / 2 -- the share of the target term
+//  "- 2 T" that the tensor-core sweep has NOT already subtracted on row j's positives)
 // 16-bit normalised operand copies: xh [N,dpad] in input order; with perm != null also xhS [N,dpad] whose row k is
 // input row perm[k], and the transpose xhT [dpad,npad] (zero padded) follows that order (perm == null: input order)
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
@@ -142,7 +150,16 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
                           int64_t dpad, int64_t row0, int64_t n, float scale, const float* rowcoef,
                           const float* colcoef, const float* gscale, float weight, int accumulate, int jsplit,
                           int fmt_bf16, float* dxh, cudaStream_t s, int self_mask = 0,
-                          const int32_t* pos_lo = nullptr, const float* pos_cnt = nullptr, const float* lam2 = nullptr);
+                          const int32_t* pos_lo = nullptr, const float* pos_cnt = nullptr, const float* lam2 = nullptr,
+                          int64_t col_begin = 0, int64_t col_end = -1, void* gt = nullptr, int64_t gt_ld = 0);
+// col_begin / col_end: sweep only the columns [col_begin, col_end) (col_begin a multiple of 256; -1 = N);
+// gt != null: also store the 16-bit coefficients transposed, gt[(column - col_begin) * gt_ld + global row]
+// Other side's gradient from such a strip (loss_grad_gemm.cu): out[ks][sidx[strip0 + r]][:] (+)= weight / gscale *
+// sum_i gt[r][i] * xhat_x[i][:] for the Ms strip rows r, the K range split over `ksplit` partial outputs
+int tc_grad_from_strip(const void* gt, int64_t gt_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
+                       int64_t npad, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale, float weight,
+                       int accumulate, int ksplit, int fmt_bf16, float* out, int64_t n_out, int num_sms,
+                       cudaStream_t s);
 // pos_lo / pos_cnt [N] (by global row), lam2 [n] (by local row): columns [pos_lo, pos_lo + pos_cnt) of row i are its
 // positives (T_ij = 1) and the epilogue subtracts lam2_i from G~ there before the 16-bit rounding
 // self_mask = 1 (all four launchers above): the operands are the SAME feature set and the entries whose global row

@@ -177,7 +177,7 @@ template <typename T, bool VEC>
 __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restrict__ inv,
                                   const int32_t* __restrict__ skey, const int32_t* __restrict__ sidx,
                                   const float* __restrict__ cnt, int64_t N, int64_t d, int64_t row0, int64_t n,
-                                  float* __restrict__ Q) {
+                                  float* __restrict__ Q, const float* __restrict__ lam2) {
     const int64_t p = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= N) return;
@@ -198,7 +198,7 @@ __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restri
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int m = 0; m < members; ++m) {
                 const int64_t j = sidx[p + m];
-                const float iv = inv[j];
+                const float iv = inv[j] * (lam2 ? 1.f - 0.5f * lam2[j] : 1.f);
                 float v[8];
                 load8(x + j * d + c, v);
 #pragma unroll
@@ -211,7 +211,7 @@ __global__ void class_sums_kernel(const T* __restrict__ x, const float* __restri
             float acc = 0.f;
             for (int m = 0; m < members; ++m) {
                 const int64_t j = sidx[p + m];
-                acc += load_as_float(x + j * d, c) * inv[j];
+                acc += load_as_float(x + j * d, c) * inv[j] * (lam2 ? 1.f - 0.5f * lam2[j] : 1.f);
             }
             qr[c] = acc;
         }
@@ -252,7 +252,7 @@ __global__ void make_operands_kernel(const T* __restrict__ x, const float* __res
         for (int k = 0; k < 4; ++k) w[k] = pack2_operand16(v[2 * k], v[2 * k + 1], fmt_bf16);
         *reinterpret_cast<uint4*>(&tile[rr][ch * 8]) = pk;
         if (row < N && col < dpad) {
-            *reinterpret_cast<uint4*>(xh + src * dpad + col) = pk;
+            if (xh) *reinterpret_cast<uint4*>(xh + src * dpad + col) = pk;
             if (xhS) *reinterpret_cast<uint4*>(xhS + row * dpad + col) = pk;
         }
     }
@@ -573,15 +573,16 @@ int launch_gscale(const float* cnt, int64_t N, int path, float* gscale, cudaStre
 }
 
 int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int32_t* skey, const int32_t* sidx,
-                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s) {
+                      const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, float* Q, cudaStream_t s,
+                      const float* lam2) {
     if (N == 0) return 0;
     const int64_t blocks = ceil_div(N * 32, kThreads);
     const bool vec = rows_vec8_ok<void>(x, d) && rows_vec8_ok<void>(Q, d);
     DISPATCH_DTYPE(dtype, {
         if (vec && (sizeof(T) == 2 || d % 8 == 0))
-            class_sums_kernel<T, true><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q);
+            class_sums_kernel<T, true><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q, lam2);
         else
-            class_sums_kernel<T, false><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q);
+            class_sums_kernel<T, false><<<blocks, kThreads, 0, s>>>(static_cast<const T*>(x), inv_norm, skey, sidx, cnt, N, d, row0, n, Q, lam2);
     });
     CLIBD_KERNEL_CHECK();
     return 0;

@@ -11,6 +11,7 @@ j=json.loads(open('gpurun_out/bench_$TAG.json').read().strip().splitlines()[-1])
 print('value',j['value'],'ms',j['ms_per_step'],'e2e',j['e2e'], 'clk', j['clocks'])
 print('roof', j['roofline'])
 print('roof_fwd', j.get('roofline_fwd'))
+print('roof_grad', j.get('roofline_grad'))
 if 'knn' in j: print('knn', j['knn'])
 print('cpu', j.get('cpu_baseline'))
 PY
