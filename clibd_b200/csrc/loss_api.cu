@@ -108,12 +108,12 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     if (p.shared_s) {
         const char* env = std::getenv("CLIBD_GT_STRIP_MB");
         const double budget = (env ? std::atof(env) : 2304.0) * 1048576.0;
-        p.gt_ld = round_up(N, 64);
-        int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(p.gt_ld))) / 256 * 256;
+        int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(N))) / 256 * 256;
         if (rows < 74 * 256) rows = 74 * 256;  // at least one 256-row tile per CTA pair and feature tile
         const int64_t all = round_up(N, 256);
         p.strip_rows = rows < all ? rows : all;
-        p.off_gt = take(2 * static_cast<size_t>(p.strip_rows) * p.gt_ld);
+        p.gt_ld = p.strip_rows;  // Gs[N rows][strip columns]
+        p.off_gt = take(2 * static_cast<size_t>(N) * p.gt_ld);
         for (int m = 0; m < 3; ++m) {
             p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad);
             p.off_Qw[m] = take(sizeof(float) * N * d);

@@ -26,7 +26,9 @@
 //  * all CTA pairs of a wave sweep the same columns in lockstep, so every CTA prefetches its own future
 //    TMA boxes into L2 two tiles ahead.
 //
-// Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 4-7 epilogue.
+// Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 4-11 epilogue.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_plan.h"
 #include "ptx.cuh"
@@ -64,7 +66,7 @@ constexpr int P_XKB_BYTES = 64 * 128;             // 8 KB : 64 rows x one K bloc
 constexpr int P_STAGE_BYTES = 128 * 128;          // 16 KB: up to 128 rows x one K block = 4 MMAs of 64 cycles
 constexpr int P_STAGES = 6;                       // 96 KB of streamed operands in flight
 constexpr int P_MAX_KB = PAIR_DCH / P_BK;         // 12
-constexpr int P_THREADS = 256;
+constexpr int P_THREADS = 384;                      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr uint32_t P_TMEM_S_COL = 384;
 constexpr int P_PF_DIST = 2;                      // L2 prefetch distance in column tiles
 
@@ -72,7 +74,7 @@ constexpr int P_SMEM_X = 0;                                         // resident 
 constexpr int P_SMEM_G = P_SMEM_X + P_MAX_KB * P_XKB_BYTES;         // G~: 4 K blocks x 8 KB
 constexpr int P_SMEM_RING = P_SMEM_G + (PAIR_BJ / P_BK) * P_XKB_BYTES;
 constexpr int P_SMEM_BARS = P_SMEM_RING + P_STAGES * P_STAGE_BYTES;
-constexpr int P_NUM_BARS = 2 * P_STAGES + 6;
+constexpr int P_NUM_BARS = 2 * P_STAGES + 8;
 constexpr int P_SMEM_TMEMPTR = P_SMEM_BARS + P_NUM_BARS * 8;
 constexpr int P_SMEM_TOTAL = P_SMEM_TMEMPTR + 16;
 constexpr int P_SMEM_ALLOC = P_SMEM_TOTAL;  // no alignment slack: the base is declared 1024-aligned and checked
@@ -98,7 +100,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
                      float* __restrict__ dxh, int self_mask, const int32_t* __restrict__ pos_lo,
                      const float* __restrict__ pos_cnt, const float* __restrict__ lam2, int64_t jt_lo, int64_t jt_hi,
-                     uint16_t* __restrict__ gt, int64_t gt_ld) {
+                     const __grid_constant__ CUtensorMap tm_gs, int store_g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -110,10 +112,12 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     uint64_t* empty = bars + P_STAGES;          // every CTA: the MMAs reading this stage have completed
     uint64_t* xfull = bars + 2 * P_STAGES;      // leader: resident Xhat rows of both CTAs landed
     uint64_t* st_full = xfull + 1;              // every CTA: S tile ready in TMEM
-    uint64_t* st_empty = xfull + 2;             // leader: S tile drained by both epilogues (8 warps)
-    uint64_t* g_full = xfull + 3;               // leader: G~ written by both epilogues (8 warps)
+    uint64_t* st_empty = xfull + 2;             // leader: S tile drained by both epilogues (16 warps)
+    uint64_t* g_full = xfull + 3;               // leader: G~ written by both epilogues (16 warps)
     uint64_t* g_empty = xfull + 4;              // every CTA: G~ consumed by the gradient MMAs
     uint64_t* acc_full = xfull + 5;             // every CTA: all accumulation finished
+    uint64_t* g_lfull = xfull + 6;              // local: G~ written by this CTA's 8 epilogue warps (store_g only)
+    uint64_t* g_sdone = xfull + 7;              // local: the TMA store of the G~ tile has finished reading it
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + P_SMEM_TMEMPTR);
 
     const int warp = threadIdx.x >> 5;
@@ -142,10 +146,12 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         mbar_init(xfull, 1);
         mbar_init(st_full, 1);
-        mbar_init(st_empty, 8);
-        mbar_init(g_full, 8);
+        mbar_init(st_empty, 16);
+        mbar_init(g_full, 16);
         mbar_init(g_empty, 1);
         mbar_init(acc_full, 1);
+        mbar_init(g_lfull, 8);
+        mbar_init(g_sdone, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -295,11 +301,39 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             issue_grad(jt1 - jt0 - 1);
             if (elected) umma_commit_cg2(acc_full, 3);
             __syncwarp();
-        } else if (warp >= 4) {  // ---------------- epilogue (both CTAs)
+        } else if (warp == 3 && store_g) {  // ---------------- coefficient store (both CTAs)
+            // The G~ tile the epilogue wrote for the gradient MMAs (4 K blocks of 64 rows x 128 B, SWIZZLE_128B) is
+            // also sent to global memory as it is -- rows = this CTA's 64 rows, columns = the tile's 256 columns of
+            // the strip -- for the other side's gradient GEMM (loss_grad_gemm.cu reads it as an M-major operand).
+            // No registers, no LSU instructions: one TMA store per K block.
+            const bool elected = elect_one();
+            const int32_t grow = static_cast<int32_t>(row0 + mt * PAIR_BM + rank * 64);
+            for (int64_t t = jt0; t < jt1; ++t) {
+                const int64_t tl = t - jt0;
+                mbar_wait(g_lfull, tl & 1);
+                if (elected) {
+                    const int32_t gcol = static_cast<int32_t>((t - jt_lo) * PAIR_BJ);
+#pragma unroll
+                    for (int kb2 = 0; kb2 < PAIR_BJ / P_BK; ++kb2)
+                        tma_store_2d(&tm_gs, gbuf + kb2 * P_XKB_BYTES, gcol + kb2 * P_BK, grow);
+                    bulk_commit_group();
+                    bulk_wait_group_read0();
+                    mbar_arrive(g_sdone);
+                }
+                __syncwarp();
+            }
+            if (elected) bulk_wait_group0();  // the stores are complete before the kernel ends
+            __syncwarp();
+        } else if (warp >= 4) {  // ---------------- epilogue (both CTAs), 8 warps: two per scheduler
+            // TMEM lane quadrant q = warp & 3 (hardware rule); the two warps of a quadrant split the 128 S columns a
+            // lane holds into halves ch = 0 / 1 of 64.  One epilogue warp per scheduler left the ~1400 dependent
+            // instructions per tile exposed (measured: +32 % instructions = +32 % kernel time); two interleave.
             const int q = warp & 3;
+            const int ch = (warp - 4) >> 2;
             const int tl_lane = q * 32 + lane;          // TMEM lane of this thread
             const int rloc = tl_lane & 63;              // row inside this CTA's 64-row slab
             const int h = tl_lane >> 6;                 // which half of the tile / piece columns this lane holds
+            const int cw = h * 128 + ch * 64;           // first tile column of this thread's 64-column window
             const int64_t lrow = mt * PAIR_BM + rank * 64 + rloc;
             const float gs = gscale[0];
             const float rcg = (lrow < n ? rowcoef[row0 + lrow] : 0.f) * gs;
@@ -308,7 +342,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             const uint32_t st_empty_l = mapa_u32(smem_u32(st_empty), 0);
             const uint32_t g_full_l = mapa_u32(smem_u32(g_full), 0);
-            const uint32_t rowaddr = smem_u32(gbuf) + (2 * h) * P_XKB_BYTES + rloc * 128;
+            const uint32_t rowaddr = smem_u32(gbuf) + (2 * h + ch) * P_XKB_BYTES + rloc * 128;
             // positives of this row: columns [plo, plo + plen) (the column operand is class-sorted); there the
             // epilogue emits G~ - lam2 so that the 16-bit rounding acts on the small difference when G~ -> 2 T
             // (the fp32 class-sum term of normalize_bwd carries the remaining 2 - lam2)
@@ -319,42 +353,40 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 plen = static_cast<int>(pos_cnt[row0 + lrow]);
                 l2g = lam2[lrow] * gs;
             }
-            // Column coefficients: lane l keeps those of columns l, 32+l, 64+l, 96+l of its half of the tile in
-            // registers (fetched one tile ahead) and the warp broadcasts them with shuffles -- no shared memory.
-            auto load_cc = [&](int64_t t, float (&dst)[4]) {
+            // Column coefficients: lane l keeps those of columns l and 32+l of its window in registers (fetched one
+            // tile ahead) and the warp broadcasts them with shuffles -- no shared memory.
+            auto load_cc = [&](int64_t t, float (&dst)[2]) {
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    const int64_t gj = t * PAIR_BJ + h * 128 + m * 32 + lane;
+                for (int m = 0; m < 2; ++m) {
+                    const int64_t gj = t * PAIR_BJ + cw + m * 32 + lane;
                     dst[m] = (gj < N) ? colcoef[gj] * gs : 0.f;
                 }
             };
-            float ccr[4], ccn[4] = {0.f, 0.f, 0.f, 0.f};
+            float ccr[2], ccn[2] = {0.f, 0.f};
             load_cc(jt0, ccr);
             for (int64_t t = jt0; t < jt1; ++t) {
                 const int64_t tl = t - jt0;
-                const int64_t nvalid = N - t * PAIR_BJ - h * 128;  // columns of this lane's half that exist
+                const int64_t nvalid = N - t * PAIR_BJ - cw;  // columns of this thread's window that exist
                 if (t + 1 < jt1) load_cc(t + 1, ccn);
                 TWAIT(6, mbar_wait(st_full, tl & 1));
                 tc_fence_after();
                 TMARK();
-                // pull the whole S slab of this lane into registers at once and hand the TMEM columns straight
-                // back to the MMA warp: S(t+1) can then start as soon as the gradient MMAs of tile t-1 retire
-                uint32_t v[128];
-                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
-                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+                // pull this thread's S window into registers at once and hand the TMEM columns straight back to
+                // the MMA warp: S(t+1) can then start as soon as the gradient MMAs of tile t-1 retire
+                uint32_t v[64];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32b_x32(tmem_base + lane_base + P_TMEM_S_COL + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(st_empty_l);
                 TLAP(10);
-                uint32_t packed[64];
-                // first column of this lane's half tile relative to the row's positive range
-                const int prel = static_cast<int>(t * PAIR_BJ + h * 128) - plo;
-                if (__any_sync(0xffffffffu, prel > -128 && prel < plen)) {  // rare: some row of the warp has positives here
+                uint32_t packed[32];
+                // first column of this thread's window relative to the row's positive range
+                const int prel = static_cast<int>(t * PAIR_BJ + cw) - plo;
+                if (__any_sync(0xffffffffu, prel > -64 && prel < plen)) {  // rare: some row of the warp has positives here
 #pragma unroll
-                    for (int k = 0; k < 128; k += 2) {
+                    for (int k = 0; k < 64; k += 2) {
                         const float c0 = __shfl_sync(0xffffffffu, ccr[k >> 5], k & 31);
                         const float c1 = __shfl_sync(0xffffffffu, ccr[k >> 5], (k & 31) + 1);
                         const float e0 = ex2_approx(fmaf(__uint_as_float(v[k]), a, nb));
@@ -365,7 +397,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 128; k += 2) {
+                    for (int k = 0; k < 64; k += 2) {
                         const float c0 = __shfl_sync(0xffffffffu, ccr[k >> 5], k & 31);
                         const float c1 = __shfl_sync(0xffffffffu, ccr[k >> 5], (k & 31) + 1);
                         const float e0 = ex2_approx(fmaf(__uint_as_float(v[k]), a, nb));
@@ -373,18 +405,18 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         packed[k / 2] = pack2<BF16>(e0 * (rcg + c0), e1 * (rcg + c1));
                     }
                 }
-                if (nvalid < 128) {  // ragged last tile (rare): columns that do not exist contribute nothing
+                if (nvalid < 64) {  // ragged last tile (rare): columns that do not exist contribute nothing
 #pragma unroll
-                    for (int p = 0; p < 64; ++p) {
+                    for (int p = 0; p < 32; ++p) {
                         if (2 * p >= nvalid) packed[p] = 0u;
                         else if (2 * p + 1 >= nvalid) packed[p] &= 0xFFFFu;
                     }
                 }
                 if (self_mask) {  // info-NCE on one feature set: the entry (row, row) does not exist
-                    const int64_t kd = row0 + lrow - (t * PAIR_BJ + h * 128);
-                    if (kd >= 0 && kd < 128) {
+                    const int64_t kd = row0 + lrow - (t * PAIR_BJ + cw);
+                    if (kd >= 0 && kd < 64) {
 #pragma unroll
-                        for (int p = 0; p < 64; ++p) {
+                        for (int p = 0; p < 32; ++p) {
                             if (2 * p == kd) packed[p] &= 0xFFFF0000u;
                             else if (2 * p + 1 == kd) packed[p] &= 0xFFFFu;
                         }
@@ -393,36 +425,27 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 TLAP(11);
                 // the previous G~ tile must have been consumed before it is overwritten
                 TWAIT(7, mbar_wait(g_empty, (tl & 1) ^ 1));
+                if (store_g) mbar_wait(g_sdone, (tl & 1) ^ 1);
                 TMARK();
 #pragma unroll
-                for (int kbh = 0; kbh < 2; ++kbh) {
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) {
-                        const uint32_t addr = rowaddr + kbh * P_XKB_BYTES + ((ch ^ (rloc & 7)) << 4);
-                        const int p = kbh * 32 + ch * 4;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[p]),
-                                     "r"(packed[p + 1]), "r"(packed[p + 2]), "r"(packed[p + 3])
-                                     : "memory");
-                    }
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const uint32_t addr = rowaddr + ((c8 ^ (rloc & 7)) << 4);
+                    const int p = c8 * 4;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[p]),
+                                 "r"(packed[p + 1]), "r"(packed[p + 2]), "r"(packed[p + 3])
+                                 : "memory");
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(g_full_l);
-                TLAP(12);
-                if (gt != nullptr && lrow < n) {
-                    // the same 16-bit coefficients, transposed, for the other side's gradient GEMM
-                    // (loss_grad_gemm.cu): Gt[column - strip start][row]; a warp writes 32 consecutive rows
-                    uint16_t* gp = gt + ((t - jt_lo) * PAIR_BJ + h * 128) * gt_ld + (row0 + lrow);
-#pragma unroll
-                    for (int p = 0; p < 64; ++p) {
-                        if (2 * p < nvalid) gp[(2 * p) * gt_ld] = static_cast<uint16_t>(packed[p] & 0xFFFFu);
-                        if (2 * p + 1 < nvalid) gp[(2 * p + 1) * gt_ld] = static_cast<uint16_t>(packed[p] >> 16);
-                    }
+                if (lane == 0) {
+                    mbar_arrive_cluster(g_full_l);
+                    if (store_g) mbar_arrive(g_lfull);
                 }
+                TLAP(12);
 #pragma unroll
-                for (int m = 0; m < 4; ++m) ccr[m] = ccn[m];
+                for (int m = 0; m < 2; ++m) ccr[m] = ccn[m];
             }
-            // drain the accumulators: dxh (+)= weight / gscale * acc
+            // drain the accumulators: dxh (+)= weight / gscale * acc (the two warps of a quadrant alternate chunks)
             TWAIT(8, mbar_wait(acc_full, 0));
             tc_fence_after();
             const float wgt = weight * gscale[1];
@@ -431,7 +454,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll 1
             for (int pc = 0; pc < npieces; ++pc) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < half_w; c0 += 32) {
+                for (int c0 = ch * 32; c0 < half_w; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(tmem_base + lane_base + pc * half_w + c0, v);
                     tmem_ld_wait();
@@ -531,7 +554,7 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     int npieces = 1;
     while (dpad % npieces != 0 || dpad / npieces > 256 || (dpad / npieces) % 16 != 0) ++npieces;
     const int piece_w = static_cast<int>(dpad / npieces);
-    CUtensorMap tm_x, tm_y, tm_yt;
+    CUtensorMap tm_x, tm_y, tm_yt, tm_gs;
     int rc = make_tmap_2d_16bit(&tm_x, xh_x, N, dpad, dpad, P_BK, 64, fmt_bf16);
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_y, xh_y, N, dpad, dpad, P_BK, 128, fmt_bf16);
@@ -542,6 +565,12 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     CLIBD_REQUIRE(col_begin >= 0 && col_begin % PAIR_BJ == 0 && col_begin < col_end, "bad column strip");
     const int64_t jt_lo = col_begin / PAIR_BJ, jt_hi = ceil_div(col_end, PAIR_BJ);
     const int64_t num_jt = jt_hi - jt_lo;
+    if (gt != nullptr) {  // coefficient strip [N rows, columns of this strip], pitch gt_ld
+        rc = make_tmap_2d_16bit(&tm_gs, gt, N, col_end - col_begin, gt_ld, P_BK, 64, fmt_bf16);
+        if (rc) return rc;
+    } else {
+        tm_gs = tm_x;  // unused
+    }
     const int64_t tiles_per_split = ceil_div(num_jt, jsplit);
     const uint32_t idesc_s = make_idesc_f16(PAIR_BM, PAIR_BJ, fmt_bf16 ? 1u : 0u);
     const uint32_t idesc_g = make_idesc_f16(PAIR_BM, piece_w, fmt_bf16 ? 1u : 0u);
@@ -551,7 +580,7 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
                                                piece_w, tiles_per_split, scale, idesc_s, idesc_g, rowcoef, colcoef,
                                                gscale, weight, accumulate, dxh, self_mask, pos_lo, pos_cnt,
-                                               lam2, jt_lo, jt_hi, static_cast<uint16_t*>(gt), gt_ld);
+                                               lam2, jt_lo, jt_hi, tm_gs, gt != nullptr ? 1 : 0);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

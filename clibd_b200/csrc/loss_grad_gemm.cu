@@ -5,11 +5,15 @@
 //
 //     dYhat[j, :] = sum_i G~[i, j] Xhat[i, :],
 //
-// so instead of recomputing S^T in a second sweep (2 n N d tensor flops per pair) the row sweep also writes G~
-// transposed, Gt[j, i], into a bounded strip buffer and THIS kernel runs the plain GEMM
+// so instead of recomputing S^T in a second sweep (2 n N d tensor flops per pair) the row sweep also sends its G~
+// tiles to a bounded strip buffer Gs[i, strip column] (TMA stores of the tiles it built for its own gradient MMAs)
+// and THIS kernel runs the plain GEMM
 //
-//     dYhat[strip rows, d] = Gt[strip rows, K = N] * XhatT[d, K = N]^T
+//     dYhat[strip columns, d] = Gs^T [M = strip columns, K = N rows] * XhatT[d, K = N]^T
 //
+// with Gs^T taken as an M-MAJOR A operand: the TMA box is 64 strip columns (128 B) x 64 rows, which is exactly
+// the canonical MN-major SWIZZLE_128B layout of tcgen05 (8-row atoms 1024 B apart along K) -- no transposition
+// anywhere.  The GEMM runs
 // on CTA pairs: 256 x 256 output tiles, tcgen05 cta_group::2 M = 256, the K range split into `ksplit` partial
 // outputs so that the (row tile, feature tile, K part) work items fill whole waves of 74 pairs.  Per 128-cycle
 // MMA a CTA reads 4 KB of A and 4 KB of B and TMA writes 8 KB: 128 B/cycle, the shared-memory bandwidth
@@ -28,7 +32,7 @@ namespace {
 using namespace ptx;
 
 constexpr int G_BK = 64;
-constexpr int G_A_BYTES = 128 * G_BK * 2;   // 16 KB: this CTA's 128 strip rows of Gt, one K block
+constexpr int G_A_BYTES = 128 * G_BK * 2;   // 16 KB: this CTA's 128 strip columns of Gs x 64 rows, as two 64-column boxes
 constexpr int G_B_BYTES = 128 * G_BK * 2;   // 16 KB: this CTA's 128 feature rows of XhatT (half of the tile's columns)
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_STAGES = 6;
@@ -118,7 +122,8 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                 if (elected) {
                     uint8_t* sa = smem + slot * G_STAGE_BYTES;
                     if (leader) mbar_arrive_expect_tx(&full[slot], 2u * G_STAGE_BYTES);
-                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa, kb * G_BK, arow, kEvictNormal);
+                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa, arow, kb * G_BK, kEvictFirst);
+                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa + G_A_BYTES / 2, arow + 64, kb * G_BK, kEvictFirst);
                     tma_load_2d_cg2(&tm_xt, full_l0 + slot * 8, sa + G_A_BYTES, kb * G_BK, brow, kEvictNormal);
                 }
                 __syncwarp();
@@ -132,7 +137,9 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
         int slot = 0;
         uint32_t phase = 0;
         uint32_t itc = 0;
-        const uint64_t d0 = make_sw128_kmajor_desc(smem_u32(smem));
+        // A: M-major (two 64-column groups 8 KB apart, K = 16 step = 2 atoms = 2048 B); B: K-major
+        const uint64_t da0 = make_sw128_mnmajor_desc(smem_u32(smem), G_A_BYTES / 2);
+        const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem + G_A_BYTES));
         const bool elected = elect_one();
         for (int64_t t = pair; t < num_items; t += num_pairs, ++itc) {
             const GItem it = g_item(t, num_nt, ksplit);
@@ -147,12 +154,12 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
                 if (elected) {
-                    const uint64_t da = d0 + slot * (G_STAGE_BYTES >> 4);
-                    const uint64_t db = da + (G_A_BYTES >> 4);
+                    const uint64_t da = da0 + slot * (G_STAGE_BYTES >> 4);
+                    const uint64_t db = db0 + slot * (G_STAGE_BYTES >> 4);
                     umma_f16_cg2(d_tmem, da, db, idesc, kb > kb0 ? 1u : 0u);
-                    umma_f16_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
-                    umma_f16_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
-                    umma_f16_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+                    umma_f16_cg2(d_tmem, da + 128, db + 2, idesc, 1u);
+                    umma_f16_cg2(d_tmem, da + 256, db + 4, idesc, 1u);
+                    umma_f16_cg2(d_tmem, da + 384, db + 6, idesc, 1u);
                     umma_commit_cg2(&empty[slot], 3);
                     if (kb == kb1 - 1) umma_commit_cg2(&tfull[as], 3);
                 }
@@ -233,15 +240,15 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
 
 }  // namespace
 
-int tc_grad_from_strip(const void* gt, int64_t gt_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
+int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
                        int64_t npad, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale, float weight,
                        int accumulate, int ksplit, int fmt_bf16, float* out, int64_t n_out, int num_sms,
                        cudaStream_t s) {
     if (Ms == 0 || N == 0) return 0;
-    CLIBD_REQUIRE(ksplit >= 1 && gt_ld % 8 == 0, "bad strip geometry");
+    CLIBD_REQUIRE(ksplit >= 1 && gs_ld % 8 == 0 && gs_ld >= Ms, "bad strip geometry");
     CUtensorMap tm_g, tm_xt;
-    // Gt [Ms rows, N columns (pitch gt_ld)]: columns beyond N read as zero (TMA out-of-bounds fill)
-    int rc = make_tmap_2d_16bit(&tm_g, gt, Ms, N, gt_ld, G_BK, 128, fmt_bf16);
+    // Gs [N rows, Ms strip columns (pitch gs_ld)]: rows beyond N / columns beyond Ms read as zero (TMA fill)
+    int rc = make_tmap_2d_16bit(&tm_g, gs, N, Ms, gs_ld, 64, G_BK, fmt_bf16);
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_xt, xhT_x, dpad, N, npad, G_BK, 128, fmt_bf16);
     if (rc) return rc;
@@ -261,7 +268,7 @@ int tc_grad_from_strip(const void* gt, int64_t gt_ld, int64_t Ms, int64_t strip0
     const int64_t items = ceil_div(Ms, 256) * ceil_div(d, G_TN) * ksplit;
     const int64_t max_pairs = num_sms / 2;
     const int pairs = static_cast<int>(items < max_pairs ? items : max_pairs);
-    const uint32_t idesc = make_idesc_f16(256, G_TN, fmt_bf16 ? 1u : 0u);
+    const uint32_t idesc = make_idesc_f16(256, G_TN, fmt_bf16 ? 1u : 0u, /*a_mn_major=*/1u);
     ProfScope prof(PROF_LOSS_GRAD_GEMM, s);
     loss_grad_gemm_kernel<<<2 * pairs, G_THREADS, G_SMEM_TOTAL, s>>>(tm_g, tm_xt, Ms, strip0, N, d, d, n_out, num_kb, ksplit,
                                                                    kb_per_split, idesc, sidx, gscale, weight, accumulate,

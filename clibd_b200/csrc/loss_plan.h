@@ -153,10 +153,10 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
                           const int32_t* pos_lo = nullptr, const float* pos_cnt = nullptr, const float* lam2 = nullptr,
                           int64_t col_begin = 0, int64_t col_end = -1, void* gt = nullptr, int64_t gt_ld = 0);
 // col_begin / col_end: sweep only the columns [col_begin, col_end) (col_begin a multiple of 256; -1 = N);
-// gt != null: also store the 16-bit coefficients transposed, gt[(column - col_begin) * gt_ld + global row]
+// gt != null: also store the 16-bit coefficient tiles, gt[global row * gt_ld + (column - col_begin)] (TMA stores)
 // Other side's gradient from such a strip (loss_grad_gemm.cu): out[ks][sidx[strip0 + r]][:] (+)= weight / gscale *
-// sum_i gt[r][i] * xhat_x[i][:] for the Ms strip rows r, the K range split over `ksplit` partial outputs
-int tc_grad_from_strip(const void* gt, int64_t gt_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
+// sum_i gs[i][r] * xhat_x[i][:] for the Ms strip columns r, the K range split over `ksplit` partial outputs
+int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
                        int64_t npad, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale, float weight,
                        int accumulate, int ksplit, int fmt_bf16, float* out, int64_t n_out, int num_sms,
                        cudaStream_t s);

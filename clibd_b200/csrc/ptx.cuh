@@ -260,6 +260,30 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
+// MN-major operand tile: the TMA box has 64 M/N elements (128 B) in its inner extent and K rows in the outer one, so
+// shared memory holds swizzle atoms of 8 K-rows x 128 B (1024 B apart along K: SBO); the next 64 M/N elements
+// start `lbo_bytes` further (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, cute
+// mma_traits_sm100.hpp make_umma_desc<Major::MN>).  One K = 16 step advances the start address by 2048 B.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// TMA store of a shared-memory box (written by st.shared + fence.proxy.async) to global memory, bulk-group tracked
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t crd0, int32_t crd1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Advance the start address by `bytes` (K sub-steps of 32 B inside the 128 B swizzle atom,
 // or whole tiles); bytes must be a multiple of 16.
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
@@ -269,8 +293,10 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) 
 // tcgen05 instruction descriptor, kind::f16, f32 accumulate, both operands K-major.
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t fmt /*0=f16,1=bf16*/) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t fmt /*0=f16,1=bf16*/,
+                                                      uint32_t a_mn_major = 0) {
+    // bit 15: A operand is MN-major (M contiguous in shared memory) instead of K-major
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
