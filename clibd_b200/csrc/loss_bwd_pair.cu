@@ -16,6 +16,15 @@
 // computed ONCE per sweep (the single-CTA kernel in loss_tc.cu needs two 384-wide chunks, i.e. computes S twice).
 // The G~ tile never crosses CTAs: each CTA feeds its own rows as the A operand.
 //
+// Two additions to the epilogue (8 warps, two per scheduler, 64 S columns per thread):
+//   * positives: the column operand is class-sorted, so row i's positives are the columns [pos_lo_i, pos_lo_i +
+//     cnt_i); there G~ - lam2_i is formed in fp32 BEFORE the 16-bit rounding (trained regime: G~ -> 2 T);
+//   * store_g (single-GPU backward, loss_api.cu backward_shared_s): the G~ tile is also TMA-stored to a strip
+//     buffer by the otherwise idle warp 3, and the other side's gradient becomes a plain GEMM over that strip
+//     (loss_grad_gemm.cu) instead of a second sweep that recomputes S^T.  Measured at N = 32768: the sweep goes
+//     from 2.65 to ~3.05 ms (half of it the 2.1 GB of extra HBM writes), the GEMM costs 1.18 ms, a second sweep
+//     2.65 ms.
+//
 // Measured constraints that shaped the code (ncu + clock64 instrumentation, see profiles/):
 //  * shared-memory bandwidth is the ceiling: per 64-cycle MMA a CTA's tensor core reads 2 KB of A and 4 KB of
 //    B (96 B/cycle) while TMA writes the next operands (64 B/cycle); nothing else may use shared memory in the
@@ -26,7 +35,8 @@
 //  * all CTA pairs of a wave sweep the same columns in lockstep, so every CTA prefetches its own future
 //    TMA boxes into L2 two tiles ahead.
 //
-// Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 4-11 epilogue.
+// Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 3 coefficient store,
+// 4-11 epilogue.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -315,7 +325,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     const int32_t gcol = static_cast<int32_t>((t - jt_lo) * PAIR_BJ);
 #pragma unroll
                     for (int kb2 = 0; kb2 < PAIR_BJ / P_BK; ++kb2)
-                        tma_store_2d(&tm_gs, gbuf + kb2 * P_XKB_BYTES, gcol + kb2 * P_BK, grow);
+                        tma_store_2d(&tm_gs, gbuf + kb2 * P_XKB_BYTES, gcol + kb2 * P_BK, grow, kEvictFirst);
                     bulk_commit_group();
                     bulk_wait_group_read0();
                     mbar_arrive(g_sdone);

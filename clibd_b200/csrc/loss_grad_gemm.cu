@@ -122,9 +122,9 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                 if (elected) {
                     uint8_t* sa = smem + slot * G_STAGE_BYTES;
                     if (leader) mbar_arrive_expect_tx(&full[slot], 2u * G_STAGE_BYTES);
-                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa, arow, kb * G_BK, kEvictFirst);
-                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa + G_A_BYTES / 2, arow + 64, kb * G_BK, kEvictFirst);
-                    tma_load_2d_cg2(&tm_xt, full_l0 + slot * 8, sa + G_A_BYTES, kb * G_BK, brow, kEvictNormal);
+                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa, arow, kb * G_BK, kEvictNormal);
+                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa + G_A_BYTES / 2, arow + 64, kb * G_BK, kEvictNormal);
+                    tma_load_2d_cg2(&tm_xt, full_l0 + slot * 8, sa + G_A_BYTES, kb * G_BK, brow, kEvictLast);
                 }
                 __syncwarp();
                 if (++slot == G_STAGES) {

@@ -274,10 +274,11 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
     return d;
 }
 // TMA store of a shared-memory box (written by st.shared + fence.proxy.async) to global memory, bulk-group tracked
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t crd0, int32_t crd1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t crd0, int32_t crd1,
+                                             uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
-                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "l"(hint)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
