@@ -212,6 +212,29 @@ def test_full_size_properties_n32768():
     assert abs(ds2 - 1024.0 * ds) <= 1e-5 * abs(ds2)
 
 
+@pytest.mark.parametrize("N,nmod,labels_kind", [(20480, 2, "multi"), (4096 + 77, 3, "zipf")])
+def test_shared_s_backward_matches_two_sweeps(monkeypatch, N, nmod, labels_kind):
+    """Single-GPU backward (S computed once per pair: row sweep + TMA-stored coefficient strip + gradient GEMM,
+    loss_api.cu backward_shared_s) against the two-sweep backward every rank of a sharded job runs, on the same
+    inputs: identical loss, gradients within the 16-bit operand tolerance.  N = 20480 with a small strip budget
+    needs two coefficient strips (18944 + 1536 columns); N = 4173 is ragged in every tile dimension."""
+    import clibd_b200 as cb
+    dev = torch.device("cuda:0")
+    feats, labels = _synthetic(N, 768, nmod, labels_kind, seed=31, dtype=torch.bfloat16)
+    feats = [None if f is None else f.float().to(dev) for f in feats]   # fp32 leaves: no output rounding
+    labels = labels.to(dev)
+    scale = torch.tensor(1 / 0.07, device=dev)
+    mod = cb.ContrastiveLoss(None, 1 / 0.07, tensor_core_operands="bf16")
+    monkeypatch.setenv("CLIBD_GT_STRIP_MB", "64")
+    shared = _run(mod, feats, labels, scale)
+    monkeypatch.setenv("CLIBD_BWD_TWO_SWEEPS", "1")
+    two = _run(mod, feats, labels, scale)
+    assert shared[0] == two[0]
+    for i in range(nmod):
+        assert _rel(shared[1][i], two[1][i]) < 5e-4, i
+    assert abs(shared[2] - two[2]) <= 1e-3 * abs(two[2])
+
+
 def test_errors_and_edge_cases():
     import clibd_b200 as cb
     dev = torch.device("cuda:0")
