@@ -26,7 +26,7 @@ SIGNATURES = {
     "clibd_profile_read": (_INT, [_P, _P]),
     "clibd_row_inv_norm": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
-    "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P,
+    "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _INT, _P, _I64, _P, _P,
                                         _P, _P]),
     "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P, _P]),
@@ -79,7 +79,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.clibd_abi_version() != 4:
+    if lib.clibd_abi_version() != 5:
         raise RuntimeError("clibd_b200: ABI version mismatch")
     _lib = lib
     return lib

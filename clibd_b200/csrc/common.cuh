@@ -110,4 +110,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+
+// Device-resident logit scale: when an entry point has one (a tensor scale, see clibd_loss_forward_stats), every
+// kernel of that call reads the scale from this pointer instead of its float argument -- no host read per step.
+// Host side: thread-local, set for the duration of one extern "C" call.
+const float* scale_dev_ptr();
+struct ScaleScope {
+    explicit ScaleScope(const float* p);
+    ~ScaleScope();
+    const float* prev_;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ float eff_scale(float s, const float* dev) { return dev ? __ldg(dev) : s; }
+#endif
+
 }  // namespace clibd

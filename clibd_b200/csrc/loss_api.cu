@@ -16,6 +16,18 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }
 
+static thread_local const float* g_scale_dev = nullptr;
+const float* scale_dev_ptr() { return g_scale_dev; }
+ScaleScope::ScaleScope(const float* p) : prev_(g_scale_dev) { g_scale_dev = p; }
+ScaleScope::~ScaleScope() { g_scale_dev = prev_; }
+
+// cell[0] = the call's logit scale (from the device scalar when given), NaN when outside (0, 43]: a tensor scale
+// cannot raise on the host without a device -> host read, so an invalid one poisons the loss instead
+__global__ void scale_set_kernel(float value, const float* __restrict__ dev, float* __restrict__ cell) {
+    const float s = dev ? dev[0] : value;
+    cell[0] = (s > 0.f && s <= 43.0f) ? s : __int_as_float(0x7fc00000);
+}
+
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -81,6 +93,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     p.off_rep = take(sizeof(int32_t) * N);
     p.off_cnt = take(sizeof(float) * N);
     p.off_gscale = take(sizeof(float) * 4);
+    p.off_scale = take(sizeof(float) * 4);
     for (int m = 0; m < 3; ++m) {
         p.off_Q[m] = take(sizeof(float) * N * d);
         p.off_dxh[m] = take(sizeof(float) * p.jsplit * n * d);
@@ -246,8 +259,8 @@ static int backward_shared_s(const void* const x[3], int dtype, const float* con
         if ((rc = launch_normalize_bwd(a, stream))) return rc;
         ++n_mod_used;
     }
-    return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * N, 0.5 / static_cast<double>(logit_scale), red,
-                                dscale_partial, stream);
+    return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * N, 0.5, red, dscale_partial, stream,
+                                scale_dev_ptr());
 }
 
 }  // namespace clibd
@@ -307,22 +320,23 @@ int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, i
 
 int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
                              const int64_t* labels, int64_t N, int64_t d, int64_t row0, int64_t n,
-                             float logit_scale, const float pair_weight[3], int path, void* scratch,
-                             int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
+                             float logit_scale, const float* logit_scale_dev, const float pair_weight[3], int path,
+                             void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
                              clibd_stream_t stream) {
     const LossPlan plan = make_loss_plan(N, n, d, path);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(labels && rowsum && colsum && pos, "null output pointer");
     const bool tc = path != PATH_SIMT_F32;
-    if (tc) {
-        CLIBD_REQUIRE(clibd_device_supported(), "tcgen05 path needs a compute-capability 10.x device");
-        // exp(S - s) must not underflow for the whole row: |S| <= s, so 2*s*log2(e) must stay < 126
-        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f,
-                      "tcgen05 path supports 0 < logit_scale <= 43 (fixed-shift softmax); use path 0");
-    } else {
-        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f, "logit_scale must be in (0, 43]");
-    }
+    if (tc) CLIBD_REQUIRE(clibd_device_supported(), "tcgen05 path needs a compute-capability 10.x device");
+    // exp(S - s) must not underflow for the whole row: |S| <= s, so 2*s*log2(e) must stay < 126.  A host value is
+    // checked here; a device scalar is checked by scale_set_kernel (NaN loss when out of range).
+    if (logit_scale_dev == nullptr)
+        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f, "logit_scale must be in (0, 43] (fixed-shift softmax)");
+    float* scale_cell = at<float>(scratch, plan.off_scale);
+    scale_set_kernel<<<1, 1, 0, stream>>>(logit_scale, logit_scale_dev, scale_cell);
+    CLIBD_KERNEL_CHECK();
+    ScaleScope scale_scope(scale_cell);  // every kernel below (and in finish / backward) reads the scale from there
     const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
     int32_t* rep = at<int32_t>(scratch, plan.off_rep);
     float* cnt = at<float>(scratch, plan.off_cnt);
@@ -403,6 +417,7 @@ int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale
     const LossPlan plan = make_loss_plan(N, n, d, path);
     CLIBD_REQUIRE(scratch && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
     CLIBD_REQUIRE(rowsum && colsum && pos && loss_out, "null pointer");
+    ScaleScope scale_scope(at<float>(scratch, plan.off_scale));  // written by clibd_loss_forward_stats
     return launch_loss_finish(N, logit_scale, pair_weight, at<float>(scratch, plan.off_cnt), rowsum, colsum, pos,
                               at<float>(scratch, plan.off_u), at<float>(scratch, plan.off_v),
                               at<double>(scratch, plan.off_red), loss_out, stream);
@@ -417,6 +432,7 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(dscale_partial != nullptr, "null dscale_partial");
+    ScaleScope scale_scope(at<float>(scratch, plan.off_scale));  // written by clibd_loss_forward_stats
     if (plan.shared_s)
         return backward_shared_s(x, dtype, inv_norm, N, d, logit_scale, pair_weight, path, scratch, plan, grad_feat_scale,
                                  grad_feat_scale_dev, dx, dscale_partial, stream);
@@ -512,8 +528,8 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
         ++n_mod_used;
     }
     // dL/ds = (1 / (2 s)) * sum over modalities and rows of xhat_i . dxhat_i  (unit upstream grad)
-    if ((rc = launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5 / static_cast<double>(logit_scale), red,
-                                   dscale_partial, stream))) return rc;
+    if ((rc = launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5, red, dscale_partial, stream,
+                                   scale_dev_ptr()))) return rc;
     return 0;
 }
 

@@ -110,7 +110,8 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
                      float* __restrict__ dxh, int self_mask, const int32_t* __restrict__ pos_lo,
                      const float* __restrict__ pos_cnt, const float* __restrict__ lam2, int64_t jt_lo, int64_t jt_hi,
-                     const __grid_constant__ CUtensorMap tm_gs, int store_g) {
+                     const __grid_constant__ CUtensorMap tm_gs, int store_g, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -590,7 +591,7 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     kern<<<grid, P_THREADS, P_SMEM_ALLOC, s>>>(tm_x, tm_y, tm_yt, N, d, d, row0, n, static_cast<int>(dpad / P_BK), npieces,
                                                piece_w, tiles_per_split, scale, idesc_s, idesc_g, rowcoef, colcoef,
                                                gscale, weight, accumulate, dxh, self_mask, pos_lo, pos_cnt,
-                                               lam2, jt_lo, jt_hi, tm_gs, gt != nullptr ? 1 : 0);
+                                               lam2, jt_lo, jt_hi, tm_gs, gt != nullptr ? 1 : 0, scale_dev_ptr());
     CLIBD_KERNEL_CHECK();
     return 0;
 }

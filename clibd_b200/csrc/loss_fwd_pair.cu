@@ -52,7 +52,8 @@ __device__ __forceinline__ void pair_tile_coords(int64_t t, int64_t num_mt, int6
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
 loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int64_t N,
                      int64_t row0, int64_t n, int num_kb, float scale, uint32_t idesc, float* __restrict__ rowpart,
-                     float* __restrict__ colpart, int self_mask) {
+                     float* __restrict__ colpart, int self_mask, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -266,7 +267,7 @@ int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t d
     const uint32_t idesc = make_idesc_f16(256, Q_TN, fmt_bf16 ? 1u : 0u);
     ProfScope prof(PROF_LOSS_FWD_TC, s);
     loss_fwd_pair_kernel<<<2 * pairs, Q_THREADS, Q_SMEM_TOTAL, s>>>(tm_a, tm_b, N, row0, n, static_cast<int>(dpad / Q_BK),
-                                                                  scale, idesc, rowpart, colpart, self_mask);
+                                                                  scale, idesc, rowpart, colpart, self_mask, scale_dev_ptr());
     CLIBD_KERNEL_CHECK();
     return 0;
 }

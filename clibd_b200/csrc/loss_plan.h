@@ -28,7 +28,7 @@ struct LossPlan {
     int jsplit = 1;          // backward: column range split across CTAs (partials summed later)
     int64_t row_parts = 0;   // forward: number of row-sum partials per row
     int64_t col_parts = 0;   // forward: number of col-sum partials per column
-    size_t off_rep = 0, off_cnt = 0, off_gscale = 0;
+    size_t off_rep = 0, off_cnt = 0, off_gscale = 0, off_scale = 0;  // off_scale: the call's logit scale on the device
     // xh: 16-bit unit rows in INPUT order (row operand); xhS / xhT: the same rows in CLASS-SORTED order and their
     // transpose (column operands: every row's positives are then one contiguous column range)
     size_t off_xh[3] = {0, 0, 0}, off_xhS[3] = {0, 0, 0}, off_xhT[3] = {0, 0, 0}, off_Q[3] = {0, 0, 0}, off_dxh[3] = {0, 0, 0};
@@ -99,7 +99,9 @@ int launch_pos_rows(const void* xa, int dtype, const float* inv_a, const float* 
 int launch_reduce_parts(const float* part, int64_t parts, int64_t stride, int64_t len, float* out, cudaStream_t s,
                         const int32_t* scatter = nullptr);
 // out[0] = mul * sum_k in[k] in double, fixed order
-int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s);
+// (div_dev != null: additionally divided by the device scalar div_dev[0])
+int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s,
+                         const float* div_dev = nullptr);
 // loss + backward coefficients u = cnt/rowsum, v = cnt/colsum
 int launch_loss_finish(int64_t N, float scale, const float w[3], const float* cnt, const float* rowsum,
                        const float* colsum, const double* pos, float* u, float* v, double* red, float* loss_out,
@@ -118,6 +120,7 @@ struct NormBwdArgs {
     const float* lam2[2] = {nullptr, nullptr};  // [n] part of the target term already subtracted by the sweep (null: 0)
     int64_t N, d, row0, n;
     float scale, grad_scale;
+    const float* scale_dev = nullptr;  // filled by launch_normalize_bwd from the call's ScaleScope
     const float* grad_scale_dev;  // optional device scalar multiplied into grad_scale (may be null)
     void* dx;               // [n,d] in dtype, may be null
     float* dots;            // [n]

@@ -19,7 +19,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float* __restrict__ inv_a,
                 const float* __restrict__ inv_b, int64_t N, int64_t d, int64_t row0, int64_t n, float scale,
-                float* __restrict__ rowpart, float* __restrict__ colpart, int self_mask) {
+                float* __restrict__ rowpart, float* __restrict__ colpart, int self_mask,
+                const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     __shared__ float As[KT][T64 + 1];
     __shared__ float Bs[KT][T64 + 1];
     __shared__ float red[T64][17];
@@ -105,7 +107,8 @@ __global__ void __launch_bounds__(256)
 simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ inv_x,
                 const float* __restrict__ inv_y, int64_t N, int64_t d, int64_t row0, int64_t n, float scale,
                 const float* __restrict__ rowcoef, const float* __restrict__ colcoef, float weight, int accumulate,
-                float* __restrict__ dxh, int self_mask) {
+                float* __restrict__ dxh, int self_mask, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     __shared__ float Xs[BR][BJ + 1];
     __shared__ float Ys[BJ][BJ + 1];
     __shared__ float Gs[BR][BJ + 1];
@@ -207,7 +210,7 @@ int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* in
     dim3 grid(static_cast<unsigned>(ceil_div(N, T64)), static_cast<unsigned>(ceil_div(n, T64)));
     DISPATCH_DTYPE(dtype, (simt_fwd_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(xa), static_cast<const T*>(xb),
                                                                   inv_a, inv_b, N, d, row0, n, scale, rowpart, colpart,
-                                                                  self_mask)));
+                                                                  self_mask, scale_dev_ptr())));
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -219,7 +222,7 @@ int simt_backward_rows(const void* x, const void* y, int dtype, const float* inv
     dim3 grid(static_cast<unsigned>(ceil_div(n, BR)), static_cast<unsigned>(ceil_div(d, 256 * DQ)));
     DISPATCH_DTYPE(dtype, (simt_bwd_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(y),
                                                                   inv_x, inv_y, N, d, row0, n, scale, rowcoef, colcoef,
-                                                                  weight, accumulate, dxh, self_mask)));
+                                                                  weight, accumulate, dxh, self_mask, scale_dev_ptr())));
     CLIBD_KERNEL_CHECK();
     return 0;
 }

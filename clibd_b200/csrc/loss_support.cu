@@ -319,7 +319,9 @@ __global__ void class_lo_kernel(const int32_t* __restrict__ rep, const int32_t* 
 __global__ void sweep_prep_kernel(const float* __restrict__ rowcoef, const float* __restrict__ colcoef,
                                   const int32_t* __restrict__ sidx, const float* __restrict__ cnt,
                                   const float* __restrict__ posrow, int64_t N, int64_t row0, int64_t n, float scale,
-                                  float* __restrict__ ccS, float* __restrict__ lam2) {
+                                  float* __restrict__ ccS, float* __restrict__ lam2,
+                                  const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k < N) ccS[k] = colcoef[sidx ? sidx[k] : k];
     if (lam2 != nullptr && k < n) {
@@ -352,11 +354,12 @@ __global__ void sum_stage1_kernel(const float* __restrict__ in, int64_t len, dou
     if (threadIdx.x == 0) red[blockIdx.x] = t;
 }
 
-__global__ void sum_stage2_kernel(const double* __restrict__ red, double mul, double* __restrict__ out) {
+__global__ void sum_stage2_kernel(const double* __restrict__ red, double mul, double* __restrict__ out,
+                                  const float* __restrict__ div_dev) {
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int b = 0; b < kRedBlocks; ++b) t += red[b];
-        out[0] = t * mul;
+        out[0] = div_dev ? t * mul / static_cast<double>(div_dev[0]) : t * mul;
     }
 }
 
@@ -364,7 +367,9 @@ __global__ void sum_stage2_kernel(const double* __restrict__ red, double mul, do
 __global__ void loss_finish_stage1_kernel(int64_t N, float scale, float w0, float w1, float w2,
                                           const float* __restrict__ cnt, const float* __restrict__ rowsum,
                                           const float* __restrict__ colsum, float* __restrict__ u,
-                                          float* __restrict__ v, double* __restrict__ red) {
+                                          float* __restrict__ v, double* __restrict__ red,
+                                          const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     __shared__ double s_buf[kThreads / 32];
     const float w[3] = {w0, w1, w2};
     double acc = 0.0;
@@ -387,7 +392,8 @@ __global__ void loss_finish_stage1_kernel(int64_t N, float scale, float w0, floa
 
 __global__ void loss_finish_stage2_kernel(int64_t N, float scale, float w0, float w1, float w2,
                                           const double* __restrict__ red, const double* __restrict__ pos,
-                                          float* __restrict__ loss_out) {
+                                          float* __restrict__ loss_out, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int b = 0; b < kRedBlocks; ++b) t += red[b];
@@ -410,7 +416,7 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
     const T* xr = reinterpret_cast<const T*>(a.x) + gi * a.d;
     const float iv = a.inv_norm[gi];
     const int64_t rp = a.rep[gi];
-    const float k1 = a.scale / static_cast<float>(a.N);
+    const float k1 = eff_scale(a.scale, a.scale_dev) / static_cast<float>(a.N);
     const float gsc = a.grad_scale * (a.grad_scale_dev ? a.grad_scale_dev[0] : 1.f);
     T* dxr = a.dx ? reinterpret_cast<T*>(a.dx) + i * a.d : nullptr;
     // effective partner weights: the sweep already subtracted lam2 of the 2 on this row's positives
@@ -642,14 +648,15 @@ int launch_sweep_prep(const float* rowcoef, const float* colcoef, const int32_t*
                       cudaStream_t s) {
     if (N == 0) return 0;
     sweep_prep_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(rowcoef, colcoef, sidx, cnt, posrow, N, row0, n, scale,
-                                                               ccS, lam2);
+                                                               ccS, lam2, scale_dev_ptr());
     CLIBD_KERNEL_CHECK();
     return 0;
 }
 
-int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s) {
+int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, double* out, cudaStream_t s,
+                         const float* div_dev) {
     sum_stage1_kernel<<<kRedBlocks, kThreads, 0, s>>>(in, len, red);
-    sum_stage2_kernel<<<1, 32, 0, s>>>(red, mul, out);
+    sum_stage2_kernel<<<1, 32, 0, s>>>(red, mul, out, div_dev);
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -657,14 +664,16 @@ int launch_sum_to_double(const float* in, int64_t len, double mul, double* red, 
 int launch_loss_finish(int64_t N, float scale, const float w[3], const float* cnt, const float* rowsum,
                        const float* colsum, const double* pos, float* u, float* v, double* red, float* loss_out,
                        cudaStream_t s) {
-    loss_finish_stage1_kernel<<<kRedBlocks, kThreads, 0, s>>>(N, scale, w[0], w[1], w[2], cnt, rowsum, colsum, u, v, red);
-    loss_finish_stage2_kernel<<<1, 32, 0, s>>>(N, scale, w[0], w[1], w[2], red, pos, loss_out);
+    loss_finish_stage1_kernel<<<kRedBlocks, kThreads, 0, s>>>(N, scale, w[0], w[1], w[2], cnt, rowsum, colsum, u, v, red, scale_dev_ptr());
+    loss_finish_stage2_kernel<<<1, 32, 0, s>>>(N, scale, w[0], w[1], w[2], red, pos, loss_out, scale_dev_ptr());
     CLIBD_KERNEL_CHECK();
     return 0;
 }
 
-int launch_normalize_bwd(const NormBwdArgs& a, cudaStream_t s) {
-    if (a.n == 0) return 0;
+int launch_normalize_bwd(const NormBwdArgs& a_in, cudaStream_t s) {
+    if (a_in.n == 0) return 0;
+    NormBwdArgs a = a_in;
+    a.scale_dev = scale_dev_ptr();
     const int64_t blocks = ceil_div(a.n * 32, kThreads);
     bool vec = rows_vec8_ok<void>(a.x, a.d) && rows_vec8_ok<void>(a.dxh, a.d) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
     for (int p = 0; p < 2; ++p)

@@ -63,7 +63,8 @@ __device__ __forceinline__ void tile_coords(int64_t t, int64_t num_mt, int64_t n
 __global__ void __launch_bounds__(F_THREADS, 1)
 loss_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int64_t N,
                    int64_t row0, int64_t n, int num_kb, float scale, uint32_t idesc, float* __restrict__ rowpart,
-                   float* __restrict__ colpart) {
+                   float* __restrict__ colpart, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* colbuf = reinterpret_cast<float*>(smem + F_SMEM_COLBUF);
@@ -271,7 +272,8 @@ loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    int64_t n, int num_kb, int chunk_w, int npieces, int64_t tiles_per_split, float scale,
                    uint32_t idesc_s, uint32_t idesc_g, int fmt_bf16, const float* __restrict__ rowcoef,
                    const float* __restrict__ colcoef, const float* __restrict__ gscale, float weight, int accumulate,
-                   float* __restrict__ dxh) {
+                   float* __restrict__ dxh, const float* __restrict__ scale_dev) {
+    scale = eff_scale(scale, scale_dev);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* gbuf = smem + B_SMEM_G;
@@ -564,7 +566,7 @@ int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad,
     const uint32_t idesc = make_idesc_f16(FWD_BM, FWD_BN, fmt_bf16 ? 1u : 0u);
     ProfScope prof(PROF_LOSS_FWD_TC, s);
     loss_fwd_tc_kernel<<<grid, F_THREADS, F_SMEM_ALLOC, s>>>(tm_a, tm_b, N, row0, n, static_cast<int>(dpad / F_BK), scale,
-                                                            idesc, rowpart, colpart);
+                                                            idesc, rowpart, colpart, scale_dev_ptr());
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -609,7 +611,7 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
         loss_bwd_tc_kernel<<<grid, B_THREADS, B_SMEM_ALLOC, s>>>(
             tm_x, tm_y, tm_yt, N, d, d - dc0 * BWD_DCH, row0, n, static_cast<int>(dpad / B_BK), chunk_w, npieces,
             tiles_per_split, scale, idesc_s, idesc_g, fmt_bf16, rowcoef, colcoef, gscale, weight, accumulate,
-            dxh + dc0 * BWD_DCH);
+            dxh + dc0 * BWD_DCH, scale_dev_ptr());
         CLIBD_KERNEL_CHECK();
     }
     return 0;

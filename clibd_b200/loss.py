@@ -140,13 +140,19 @@ class _FusedClipLossFn(torch.autograd.Function):
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             stats = torch.zeros(6 * N, dtype=torch.float32, device=device)  # rowsum[3][N] | colsum[3][N]
             pos = torch.zeros(3, dtype=torch.float64, device=device)
+            # a tensor scale stays on the device: the library copies it into the scratch and every kernel of the
+            # forward and the backward reads it from there (no host read in the training step)
+            scale_dev = None
+            if scale_tensor is not None:
+                scale_dev = scale_tensor.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
             xs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in gathered])
             ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in inv])
             w = _lib.float_array3(weights)
             rowsum_ptr = stats.data_ptr()
             colsum_ptr = stats.data_ptr() + 4 * 3 * N
             _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, all_labels.data_ptr(), N, d, row0, n,
-                                                    scale_value, w, path, scratch.data_ptr(), nbytes, rowsum_ptr,
+                                                    scale_value, None if scale_dev is None else scale_dev.data_ptr(),
+                                                    w, path, scratch.data_ptr(), nbytes, rowsum_ptr,
                                                     colsum_ptr, pos.data_ptr(), stream))
             if world > 1:
                 dist.all_reduce(stats, group=group)  # row sums have disjoint support, column sums add up
@@ -229,8 +235,8 @@ def _fused_loss(image_features, dna_features, text_features, labels, logit_scale
     if n_ordered == 0:
         raise ZeroDivisionError("float division by zero")  # reference: sum([]) * 1.0 / len([])
     scale_tensor = logit_scale if isinstance(logit_scale, torch.Tensor) else None
-    # one host read when the scale is a tensor (the reference reads loss.item() every step anyway)
-    scale_value = float(logit_scale.detach()) if scale_tensor is not None else float(logit_scale)
+    # a tensor scale is handed over as a device pointer (no host read); scale_value is then unused
+    scale_value = 0.0 if scale_tensor is not None else float(logit_scale)
     path = _select_path(common, operands)
     return _FusedClipLossFn.apply(feats[0], feats[1], feats[2], labels, scale_tensor, scale_value, weights, path,
                                   group, world, rank, sum_grads)

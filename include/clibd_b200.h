@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 4
+#define CLIBD_ABI_VERSION 5
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -64,15 +64,20 @@ int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, i
  * [n_global]; labels: [n_global] int64.
  * Writes rowsum[p*n_global + i] for LOCAL rows i (sum_j exp(S_ij - s)), colsum[p*n_global + j]
  * for all j summed over the local rows only (all-reduce it across ranks), and
- * pos[p] = sum_{i local} sum_j T_ij * cos_ij (all-reduce it). */
+ * pos[p] = sum_{i local} sum_j T_ij * cos_ij (all-reduce it).
+ * logit_scale_dev: optional DEVICE scalar (the reference's learnable `logit_scale.exp()` tensor,
+ * simple_clip.py:61); when given it replaces logit_scale, is copied into the scratch and every kernel of this
+ * call, of clibd_loss_forward_finish and of clibd_loss_backward reads it from there -- no host read per step.
+ * A host value outside (0, 43] is an error; a device value outside it yields a NaN loss. */
 int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
                              const int64_t* labels, int64_t n_global, int64_t d, int64_t row0, int64_t n_local,
-                             float logit_scale, const float pair_weight[3] /* host */, int path, void* scratch,
-                             int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
-                             clibd_stream_t stream);
+                             float logit_scale, const float* logit_scale_dev, const float pair_weight[3] /* host */,
+                             int path, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
+                             double* pos, clibd_stream_t stream);
 
 /* Loss value from complete statistics (rowsum/colsum/pos now hold GLOBAL sums for all
- * n_global rows/columns); also prepares the backward coefficients inside scratch. */
+ * n_global rows/columns); also prepares the backward coefficients inside scratch.  The scale used is the one
+ * clibd_loss_forward_stats stored in the scratch (logit_scale here is informational). */
 int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, float logit_scale,
                               const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
                               const float* rowsum, const float* colsum, const double* pos, float* loss_out,

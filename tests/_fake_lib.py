@@ -49,8 +49,10 @@ class FakeLib:
             xh.append(x * iv[:, None])
         return xh
 
-    def clibd_loss_forward_stats(self, xs, dtype, ivs, labels, N, d, row0, n, scale, w, path, scratch, nbytes,
-                                 rowsum, colsum, pos, stream):
+    def clibd_loss_forward_stats(self, xs, dtype, ivs, labels, N, d, row0, n, scale, scale_dev, w, path, scratch,
+                                 nbytes, rowsum, colsum, pos, stream):
+        if scale_dev:
+            scale = float(_arr(scale_dev, (1,), np.float32)[0])
         xh = self._inputs(xs, ivs, dtype, N, d)
         lab = _arr(labels, (N,), np.int64)
         rs = _arr(rowsum, (3, N), np.float32)
@@ -66,11 +68,12 @@ class FakeLib:
             rs[p, row0:row0 + n] = E.sum(1)
             cs[p, :] = E.sum(0)
             ps[p] = cos[T].sum()
-        self.state[scratch] = {"labels": lab.copy()}
+        self.state[scratch] = {"labels": lab.copy(), "scale": scale}
         return 0
 
     def clibd_loss_forward_finish(self, N, n, d, scale, w, path, scratch, nbytes, rowsum, colsum, pos, loss_out, stream):
         st = self.state[scratch]
+        scale = st["scale"]  # the one forward_stats stored
         lab = st["labels"]
         _, inv, cnt = np.unique(lab, return_inverse=True, return_counts=True)
         c = cnt[inv].astype(np.float64)
@@ -92,6 +95,7 @@ class FakeLib:
         if gscale_dev:
             gscale = gscale * float(_arr(gscale_dev, (1,), np.float32)[0])
         st = self.state[scratch]
+        scale = st["scale"]
         xh = self._inputs(xs, ivs, dtype, N, d)
         lab = st["labels"]
         T = (lab[row0:row0 + n, None] == lab[None, :]).astype(np.float64)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()  # builds if needed, dlopens, binds every symbol
     assert os.path.exists(_build.LIB_PATH)
-    assert lib.clibd_abi_version() == 4
+    assert lib.clibd_abi_version() == 5
     assert lib.clibd_loss_scratch_bytes(4096, 512, 768, 1) > 0
     assert lib.clibd_loss_scratch_bytes(0, 0, 768, 1) == -1
     assert lib.clibd_knn_scratch_bytes(1000, 100000, 768, 5, 2) > 0

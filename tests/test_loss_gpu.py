@@ -247,6 +247,11 @@ def test_errors_and_edge_cases():
         mod(x.cpu(), x.cpu(), None, lab.cpu(), 1.0)
     with pytest.raises(ValueError, match="logit_scale"):
         mod(x, x, None, lab, 100.0)
+    # a TENSOR scale never leaves the device (no host read per step): out of range it poisons the loss instead
+    assert torch.isnan(mod(x, x, None, lab, torch.tensor(100.0, device=dev)))
+    ok_t = mod(x, x, None, lab, torch.tensor(10.0, device=dev))
+    ok_f = mod(x, x, None, lab, 10.0)
+    assert float(ok_t) == float(ok_f)
     with pytest.raises(ZeroDivisionError):
         cb.ClipLoss(bind_to="text")(x, x, None, lab, 1.0)
     with pytest.raises(NotImplementedError):
