@@ -116,7 +116,11 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     // Single-GPU tcgen05 pair path: S is computed once per pair; the row sweep stores its 16-bit coefficients
     // transposed in a strip buffer (CLIBD_GT_STRIP_MB, default 2304 MB = the whole column range at
     // N = 32768, and never fewer than 18944 columns) and the other side's gradient is a plain GEMM over that strip.
-    p.shared_s = allow_shared_s && tc && n == N && p.dpad <= PAIR_DCH && !std::getenv("CLIBD_BWD_TWO_SWEEPS") &&
+    // (below N = 6144 the step is launch-bound and the extra staging launches cost more than the sweep they save:
+    //  measured 0.88 vs 0.81 ms at N = 4096, 2.26 vs 2.56 ms at N = 8192, three modalities)
+    const char* min_env = std::getenv("CLIBD_SHARED_S_MIN_N");  // tests force the path at oracle-sized batches
+    const int64_t shared_min_n = min_env ? std::atoll(min_env) : 6144;
+    p.shared_s = allow_shared_s && tc && n == N && N >= shared_min_n && p.dpad <= PAIR_DCH && !std::getenv("CLIBD_BWD_TWO_SWEEPS") &&
                  !std::getenv("CLIBD_BWD_SINGLE");
     if (p.shared_s) {
         const char* env = std::getenv("CLIBD_GT_STRIP_MB");

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_loss_gpu.py -q -m gpu -x -k "shared_s or full_size" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_loss_gpu.py -q -m gpu --timeout 600 2>&1 | tail -8
