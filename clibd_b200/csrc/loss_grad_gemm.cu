@@ -266,7 +266,11 @@ int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0
         CLIBD_CHECK_CUDA(cudaMemsetAsync(out + static_cast<int64_t>(ksplit) * n_out * d, 0,
                                          sizeof(float) * static_cast<size_t>(slots - ksplit) * n_out * d, s));
     const int64_t items = ceil_div(Ms, 256) * ceil_div(d, G_TN) * ksplit;
-    const int64_t max_pairs = num_sms / 2;
+    // a multiple of the number of feature tiles: the pairs that work on the feature tiles of one (row tile, K part)
+    // then always run in the same wave and share the Gs blocks through L2 (74 -> 72 pairs for d = 768)
+    const int64_t num_nt = ceil_div(d, G_TN);
+    int64_t max_pairs = num_sms / 2;
+    if (max_pairs > num_nt) max_pairs -= max_pairs % num_nt;
     const int pairs = static_cast<int>(items < max_pairs ? items : max_pairs);
     const uint32_t idesc = make_idesc_f16(256, G_TN, fmt_bf16 ? 1u : 0u, /*a_mn_major=*/1u);
     ProfScope prof(PROF_LOSS_GRAD_GEMM, s);

@@ -2,7 +2,7 @@
 # One measurement pass on the GPU box: parity tests, bench, ncu launch list, ncu --set full of the tensor
 # kernels. Outputs go to gpurun_out/ (merged back by gpurun).
 mkdir -p gpurun_out
-TAG=${1:-r1k}
+TAG=${1:-r1n}
 echo "=== pytest gpu"; timeout 1200 python -m pytest tests -q -m gpu --timeout 600 -x 2>&1 | tail -4
 echo "=== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -c 300 gpurun_out/bench_$TAG.err
