@@ -22,8 +22,8 @@
 //   * store_g (single-GPU backward, loss_api.cu backward_shared_s): the G~ tile is also TMA-stored to a strip
 //     buffer by the otherwise idle warp 3, and the other side's gradient becomes a plain GEMM over that strip
 //     (loss_grad_gemm.cu) instead of a second sweep that recomputes S^T.  Measured at N = 32768: the sweep goes
-//     from 2.65 to ~3.05 ms (half of it the 2.1 GB of extra HBM writes), the GEMM costs 1.18 ms, a second sweep
-//     2.65 ms.
+//     from 2.65 to ~3.05 ms (the store itself: with the same synchronisation but no store it stays at 2.65, with
+//     the stores aimed at an L2-resident dummy region at 2.86), the GEMM costs 1.17 ms, a second sweep 2.65 ms.
 //
 // Measured constraints that shaped the code (ncu + clock64 instrumentation, see profiles/):
 //  * shared-memory bandwidth is the ceiling: per 64-cycle MMA a CTA's tensor core reads 2 KB of A and 4 KB of
