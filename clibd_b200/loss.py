@@ -91,6 +91,17 @@ def _device_ctx(device):
     return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
 
 
+def _coalesced(group):
+    """One NCCL launch for a batch of same-kind collectives (torch's coalescing manager batches
+    all_gather_into_tensor / all_reduce calls into a single grouped call); plain sequential calls elsewhere."""
+    try:
+        if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+            return dist._coalescing_manager(group=group)
+    except Exception:  # noqa: BLE001
+        pass
+    return contextlib.nullcontext()
+
+
 class _FusedClipLossFn(torch.autograd.Function):
     """forward(image, dna, text, labels, scale_tensor|None, scale_value, weights, path, group, world, rank,
     sum_grad_over_ranks) -> 0-d float32 loss"""
@@ -116,15 +127,14 @@ class _FusedClipLossFn(torch.autograd.Function):
             if world > 1:
                 N = n * world
                 all_labels = torch.empty(N, dtype=torch.int64, device=device)
-                dist.all_gather_into_tensor(all_labels, labels, group=group)
-                gathered = []
-                for f in local:
-                    if f is None:
-                        gathered.append(None)
-                        continue
-                    g = torch.empty((N, d), dtype=dtype, device=device)
-                    dist.all_gather_into_tensor(g, f, group=group)
-                    gathered.append(g)
+                gathered = [None if f is None else torch.empty((N, d), dtype=dtype, device=device) for f in local]
+                # labels + up to three feature sets in ONE grouped all-gather; a coalesced call wants one dtype, and an
+                # all-gather only concatenates bytes, so the int64 labels travel viewed as the feature dtype
+                with _coalesced(group):
+                    dist.all_gather_into_tensor(all_labels.view(dtype), labels.view(dtype), group=group)
+                    for f, g in zip(local, gathered):
+                        if f is not None:
+                            dist.all_gather_into_tensor(g, f, group=group)
                 # inverse norms of all rows from the gathered features: one 50 MB read per modality instead of one
                 # more latency-bound collective each
                 inv = [None if g is None else inv_norms(g) for g in gathered]
