@@ -34,12 +34,13 @@ def emu(feats, labels, s, kind, scheme):
     Gx = Ex*((c/rx)[:,None]+(c/qx)[None,:]) - 2*T
     dAx = Gx@Bh
     return ((dA-dAx).norm()/dAx.norm()).item()
-N,d=768,768
-for labels_kind, align in [("onehot",0.7),("multi",0.7),("multi",0.0),("onehot",0.0)]:
-    gen=torch.Generator().manual_seed(21)
-    labels = torch.arange(N) if labels_kind=="onehot" else torch.randint(0,N//4,(N,),generator=gen)
-    centres=torch.randn(N,d,generator=gen)
-    base = centres[labels] if labels_kind=="multi" else centres
-    for kind in ("bf16","fp16"):
-        feats=[rnd(align*base+(1-align)*torch.randn(N,d,generator=gen),kind) for _ in range(2)]
-        print(labels_kind, align, kind, "old", emu(feats,labels,1/0.07,kind,"old"), "new", emu(feats,labels,1/0.07,kind,"new"))
+if __name__ == "__main__":
+    N,d=768,768
+    for labels_kind, align in [("onehot",0.7),("multi",0.7),("multi",0.0),("onehot",0.0)]:
+        gen=torch.Generator().manual_seed(21)
+        labels = torch.arange(N) if labels_kind=="onehot" else torch.randint(0,N//4,(N,),generator=gen)
+        centres=torch.randn(N,d,generator=gen)
+        base = centres[labels] if labels_kind=="multi" else centres
+        for kind in ("bf16","fp16"):
+            feats=[rnd(align*base+(1-align)*torch.randn(N,d,generator=gen),kind) for _ in range(2)]
+            print(labels_kind, align, kind, "old", emu(feats,labels,1/0.07,kind,"old"), "new", emu(feats,labels,1/0.07,kind,"new"))
