@@ -332,6 +332,7 @@ def run_ours(args):
     # strip (2*n*N*d per pair, no S recompute); absent when the rows are sharded (two sweeps per pair instead)
     roofline_grad = roof(4, 2.0 * n * N * d * (prof_n[1] / prof_n[4]) if prof_n[4] else 0.0, "loss_grad_gemm_kernel")
     step_frac = (18.0 * n * N * d) / (ms_step * 1e-3) / 1e12 / peak_tf
+    burst_tf = peaks.get("bf16_tflops")
 
     out = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -339,6 +340,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "roofline_fwd": roofline_fwd, "roofline_grad": roofline_grad, "step_tensor_frac_algorithmic": step_frac,
+        # the same 18*n*N*d algorithmic flops of the whole step against the burst cuBLAS figure, for reference
+        "step_tensor_frac_algorithmic_vs_burst": (step_frac * peak_tf / burst_tf) if burst_tf else None,
     }
 
     # ---------------- kNN workload
