@@ -102,6 +102,23 @@ def test_tensor_core_path_matches_oracle(operands, N, d, nmod, labels_kind, back
     assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
 
 
+def test_wide_features_take_the_single_cta_sweep():
+    """d = 1024 > 768: the CTA-pair kernels hold at most 768 feature columns in TMEM, so the forward runs on the
+    pair kernel and the backward on the single-CTA sweep (loss_tc.cu, two 384-column chunks per 128 rows,
+    class-sorted column operand like the pair path) -- same tolerance against the oracle."""
+    import clibd_b200 as cb
+    dev = torch.device("cuda:0")
+    feats, labels = _synthetic(300, 1024, 2, "multi", seed=13, dtype=torch.bfloat16)
+    scale = torch.tensor(1 / 0.07)
+    ref = lo.contrastive_loss([None if f is None else f.float().numpy() for f in feats], labels.numpy(), float(scale))
+    mod = cb.ContrastiveLoss(torch.nn.CrossEntropyLoss(), 1 / 0.07, tensor_core_operands="bf16")
+    loss, grads, ds = _run(mod, [None if f is None else f.float().to(dev) for f in feats], labels.to(dev), scale.to(dev))
+    assert abs(loss - ref["loss"]) <= 1e-3 * abs(ref["loss"])
+    for i in range(2):
+        assert _rel(grads[i], ref["grads"][i]) < 1e-3, i
+    assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
+
+
 @pytest.mark.parametrize("operands", ["bf16", "fp16"])
 def test_tensor_core_fp32_inputs_gradient_tolerance(operands):
     """fp32 inputs forced through the tensor-core path: gradients come back in fp32, so the
