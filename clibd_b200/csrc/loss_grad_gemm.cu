@@ -35,7 +35,7 @@ constexpr int G_BK = 64;
 constexpr int G_A_BYTES = 128 * G_BK * 2;   // 16 KB: this CTA's 128 strip columns of Gs x 64 rows, as two 64-column boxes
 constexpr int G_B_BYTES = 128 * G_BK * 2;   // 16 KB: this CTA's 128 feature rows of XhatT (half of the tile's columns)
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
-constexpr int G_STAGES = 6;
+constexpr int G_STAGES = 7;
 constexpr int G_THREADS = 384;
 constexpr int G_EPI_WARPS = 8;
 constexpr int G_TN = 256;
