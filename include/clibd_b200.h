@@ -89,7 +89,10 @@ int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, floa
  * contribution to dL/d(logit_scale) for unit upstream gradient (all-reduce, then
  * multiply by the rank's own grad_output).  grad_feat_scale = sum over ranks of
  * grad_output (the reduce-scatter(SUM) convention of torch.distributed.nn.all_gather,
- * loss_func.py:97). */
+ * loss_func.py:97).  The scale used is the one clibd_loss_forward_stats stored in the scratch (logit_scale here is
+ * informational).  With n_local == n_global (one GPU) and n_global >= 6144 the backward computes S once per
+ * modality pair and passes its 16-bit coefficients to a second GEMM through a strip inside the scratch
+ * (environment: CLIBD_GT_STRIP_MB bounds the strip, CLIBD_BWD_TWO_SWEEPS=1 selects the two-sweep form). */
 int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
                         int64_t d, int64_t row0, int64_t n_local, float logit_scale,
                         const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
