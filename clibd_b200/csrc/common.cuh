@@ -28,6 +28,11 @@ struct ProfScope {
     cudaEvent_t e0_ = nullptr, e1_ = nullptr;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: set it once per
+// (kernel, device) under a mutex, so that a process that drives several GPUs, or autograd's worker thread racing
+// the main thread on first use, never launches with the 48 KB default.  Returns a cudaError_t.
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
+
 #define CLIBD_CHECK_CUDA(expr)                                                                    \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \

@@ -843,19 +843,11 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
     {
     ProfScope prof(PROF_KNN_SCREEN_TC, stream);
     if (plan.kp == 8) {
-        static bool attr8 = false;
-        if (!attr8) {
-            CLIBD_CHECK_CUDA(cudaFuncSetAttribute(knn_screen_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_ALLOC));
-            attr8 = true;
-        }
+        CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&knn_screen_tc_kernel<8>), S_SMEM_ALLOC));
         knn_screen_tc_kernel<8><<<grid, S_THREADS, S_SMEM_ALLOC, stream>>>(tm_q, tm_k, Q, K, static_cast<int>(plan.dpad / S_BK),
                                                                            plan.num_chunks, plan.tiles_per_chunk, idesc, k, floor_delta, rowfloor, cs, ci);
     } else {
-        static bool attr16 = false;
-        if (!attr16) {
-            CLIBD_CHECK_CUDA(cudaFuncSetAttribute(knn_screen_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_ALLOC));
-            attr16 = true;
-        }
+        CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&knn_screen_tc_kernel<16>), S_SMEM_ALLOC));
         knn_screen_tc_kernel<16><<<grid, S_THREADS, S_SMEM_ALLOC, stream>>>(tm_q, tm_k, Q, K, static_cast<int>(plan.dpad / S_BK),
                                                                             plan.num_chunks, plan.tiles_per_chunk, idesc, k, floor_delta, rowfloor, cs, ci);
     }

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -46,6 +47,19 @@ ProfScope::~ProfScope() {
     cudaEventRecord(e1_, s_);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_events[slot_].emplace_back(e0_, e1_);
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert({kernel, dev});
+    return e;
 }
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }

@@ -554,12 +554,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % P_BK == 0 && dpad <= PAIR_DCH, "pair backward needs a padded feature dim <= 768");
     CLIBD_REQUIRE(lam2 == nullptr || (pos_lo != nullptr && pos_cnt != nullptr), "lam2 needs the positive ranges");
-    static bool attr_set = false;
-    if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_ALLOC));
-        attr_set = true;
-    }
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_bwd_pair_kernel<true>), P_SMEM_ALLOC));
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_bwd_pair_kernel<false>), P_SMEM_ALLOC));
     // gradient pieces: npieces equal pieces of width piece_w <= 256, piece_w a multiple of 16 (8 rows of YhatT per
     // swizzle atom and per CTA)
     int npieces = 1;

@@ -256,11 +256,7 @@ int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t d
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_b, xh_b, N, dpad, dpad, Q_BK, 128, fmt_bf16);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL));
-        attr_set = true;
-    }
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_fwd_pair_kernel), Q_SMEM_TOTAL));
     const int64_t tiles = ceil_div(n, 256) * ceil_div(N, Q_TN);
     const int64_t max_pairs = num_sms / 2;
     const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);

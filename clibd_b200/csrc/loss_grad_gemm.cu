@@ -252,11 +252,7 @@ int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_xt, xhT_x, dpad, N, npad, G_BK, 128, fmt_bf16);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
-        attr_set = true;
-    }
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_grad_gemm_kernel), G_SMEM_TOTAL));
     const int num_kb = static_cast<int>(ceil_div(N, G_BK));
     const int slots = ksplit;  // the caller sums `slots` partial outputs: parts that get no K blocks are zeroed
     if (ksplit > num_kb) ksplit = num_kb;

@@ -556,11 +556,7 @@ int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad,
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_b, xh_b, N, dpad, dpad, F_BK, FWD_BN, fmt_bf16);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_ALLOC));
-        attr_set = true;
-    }
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_fwd_tc_kernel), F_SMEM_ALLOC));
     const int64_t tiles = ceil_div(n, FWD_BM) * ceil_div(N, FWD_BN);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     const uint32_t idesc = make_idesc_f16(FWD_BM, FWD_BN, fmt_bf16 ? 1u : 0u);
@@ -577,11 +573,7 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
                      cudaStream_t s) {
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % B_BK == 0, "padded feature dim must be a multiple of 64");
-    static bool attr_set = false;
-    if (!attr_set) {
-        CLIBD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_ALLOC));
-        attr_set = true;
-    }
+    CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_bwd_tc_kernel), B_SMEM_ALLOC));
     CUtensorMap tm_x, tm_y, tm_yt;
     int rc = make_tmap_2d_16bit(&tm_x, xh_x, N, dpad, dpad, B_BK, BWD_BM, fmt_bf16);
     if (rc) return rc;
