@@ -4,7 +4,9 @@ nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU
 """
 from __future__ import annotations
 
+import fcntl
 import glob
+import hashlib
 import os
 import subprocess
 import sys
@@ -13,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libclibd_b200.so")
+HASH_PATH = os.path.join(LIB_DIR, "libclibd_b200.sha256")  # hash of the sources the library was built from
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -26,13 +29,22 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
+def source_hash() -> str:
     deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
     deps += glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(deps):
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    """The library is stale when it was built from other sources than the ones in the tree (content hash, not
+    mtimes: a snapshot copied to another box keeps its binary)."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    return open(HASH_PATH).read().strip() != source_hash()
 
 
 def build_variant(name: str, defines) -> str:
@@ -48,8 +60,16 @@ def build_variant(name: str, defines) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:  # one builder at a time (one process per GPU)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
@@ -65,8 +85,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out.decode())
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB_PATH + ".tmp"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(link)
+    os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

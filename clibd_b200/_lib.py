@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import subprocess
 
 from . import _build
 
@@ -13,7 +14,9 @@ _I64 = _c.c_int64
 _INT = _c.c_int
 _F = _c.c_float
 
+ABI_VERSION = 6
 DT_F32, DT_BF16, DT_F16, DT_F64 = 0, 1, 2, 3
+MODE_LOCAL, MODE_EXCHANGE = 0, 1
 PATH_SIMT_F32, PATH_TC_BF16, PATH_TC_F16 = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol include/clibd_b200.h declares
@@ -25,11 +28,19 @@ SIGNATURES = {
     "clibd_profile_enable": (_INT, [_INT]),
     "clibd_profile_read": (_INT, [_P, _P]),
     "clibd_row_inv_norm": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
-    "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT]),
-    "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _INT, _P, _I64, _P, _P,
-                                        _P, _P]),
-    "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P, _P, _P]),
+    "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
+    "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _INT, _INT, _P, _I64, _P,
+                                        _P, _P, _P, _P]),
+    "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P, _P]),
+    "clibd_loss_backward_sweeps": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P,
+                                          _INT, _INT, _P]),
+    "clibd_loss_backward_finish": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _F, _P,
+                                          _INT, _P, _P, _P]),
+    "clibd_shard_push_rows": (_INT, [_P, _INT, _P, _I64, _I64, _INT, _INT, _P, _P, _P, _P]),
+    "clibd_shard_push_stats": (_INT, [_P, _P, _I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P]),
+    "clibd_shard_reduce_stats": (_INT, [_P, _P, _I64, _INT, _P, _P, _P]),
+    "clibd_shard_push_floats": (_INT, [_P, _I64, _INT, _INT, _P, _P]),
     "clibd_knn_normalize": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_knn_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
     "clibd_knn_search": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P]),
@@ -63,7 +74,8 @@ def lib_path() -> str:
 
 
 def load():
-    """Load (building first if the sources are newer) the shared library."""
+    """Load the shared library, rebuilding it first when the sources in the tree differ from the ones it was built
+    from (content hash, clibd_b200/_build.py)."""
     global _lib
     if _test_double is not None:
         return _test_double
@@ -71,15 +83,20 @@ def load():
         return _lib
     path = os.environ.get("CLIBD_B200_LIB")  # development: an instrumented build of the same sources
     if not path:
-        path = _build.LIB_PATH
-        if not os.path.exists(path) or os.environ.get("CLIBD_B200_REBUILD"):
-            path = _build.build()
+        # rebuilds when a source is newer than the library (or CLIBD_B200_REBUILD is set); a fresh checkout on a box
+        # without nvcc keeps the shipped binary
+        try:
+            path = _build.build(force=bool(os.environ.get("CLIBD_B200_REBUILD")))
+        except (OSError, RuntimeError, subprocess.SubprocessError):
+            path = _build.LIB_PATH
+            if not os.path.exists(path):
+                raise
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.clibd_abi_version() != 5:
+    if lib.clibd_abi_version() != ABI_VERSION:
         raise RuntimeError("clibd_b200: ABI version mismatch")
     _lib = lib
     return lib
@@ -106,4 +123,19 @@ def float_array3(vals):
     arr = (_F * 3)()
     for i, v in enumerate(vals):
         arr[i] = float(v)
+    return arr
+
+
+def ptr_array(ptrs):
+    """host array of device pointers (None -> NULL)"""
+    arr = (_P * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = _P(p) if p else _P(None)
+    return arr
+
+
+def int_array(vals):
+    arr = (_INT * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
     return arr

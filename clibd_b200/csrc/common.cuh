@@ -129,4 +129,15 @@ struct ScaleScope {
 __device__ __forceinline__ float eff_scale(float s, const float* dev) { return dev ? __ldg(dev) : s; }
 #endif
 
+// Shift of the softmax sums: every kernel forms e_ij = exp(S_ij - shift) ONCE and uses it for the row sums, the
+// column sums and the gradient coefficients e_ij (c_i / r_i + c_j / q_j), which do not depend on the shift.  With
+// unit rows |S_ij| <= s.  While s <= 43 the shift is s itself: every term is <= 1 and even S_ij = -s stays above the
+// float32 underflow (2 s log2(e) < 126).  The reference never clamps its learnable logit_scale (simple_clip.py:32,61),
+// so beyond 43 the shift stays at 43 (at s - 70 from s = 113): terms grow up to exp(70), sums of 2^18 of them stay
+// finite, and the entries that underflow are those with S_ij < shift - 87, i.e. more than e^-87 below the largest
+// representable term -- they cannot matter to a row whose best logit is representable.  A row (or column) whose sum
+// underflows entirely (every cosine below (shift - 87) / s) is clamped to 1e-30 instead of producing log(0).
+__host__ __device__ inline float softmax_shift(float s) { return s <= 43.f ? s : fmaxf(43.f, s - 70.f); }
+constexpr float kMinSoftmaxSum = 1e-30f;
+
 }  // namespace clibd

@@ -83,7 +83,7 @@ int check_args(const void* z, const float* inv_norm, int dtype, int64_t M, int64
     CLIBD_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, "dtype must be 0, 1 or 2");
     CLIBD_REQUIRE(path >= 0 && path <= 2, "path must be 0, 1 or 2");
     // fixed-shift softmax exp(S - s): |S| <= s for unit rows, 2 s log2(e) must stay below 126
-    CLIBD_REQUIRE(scale > 0.f && scale <= 43.0f, "1 / temperature must be in (0, 43]");
+    CLIBD_REQUIRE(scale > 0.f && scale < 1e30f, "1 / temperature must be a positive finite number");
     CLIBD_REQUIRE(scratch != nullptr && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
     if (path != PATH_SIMT_F32) {
         CLIBD_REQUIRE(clibd_device_supported(), "tcgen05 path needs a compute-capability 10.x device");

@@ -22,11 +22,13 @@ const float* scale_dev_ptr() { return g_scale_dev; }
 ScaleScope::ScaleScope(const float* p) : prev_(g_scale_dev) { g_scale_dev = p; }
 ScaleScope::~ScaleScope() { g_scale_dev = prev_; }
 
-// cell[0] = the call's logit scale (from the device scalar when given), NaN when outside (0, 43]: a tensor scale
-// cannot raise on the host without a device -> host read, so an invalid one poisons the loss instead
+// cell[0] = the call's logit scale (from the device scalar when given), NaN when it is not a positive finite number:
+// a tensor scale cannot raise on the host without a device -> host read, so an invalid one poisons the loss instead.
+// There is no upper limit: the reference never clamps its learnable logit_scale (simple_clip.py:32,61) and the kernels
+// pick their softmax shift from the scale (common.cuh: softmax_shift).
 __global__ void scale_set_kernel(float value, const float* __restrict__ dev, float* __restrict__ cell) {
     const float s = dev ? dev[0] : value;
-    cell[0] = (s > 0.f && s <= 43.0f) ? s : __int_as_float(0x7fc00000);
+    cell[0] = (s > 0.f && s < 1e30f) ? s : __int_as_float(0x7fc00000);
 }
 
 static std::atomic<int64_t> g_launches{0};
@@ -64,7 +66,7 @@ cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_shared_s) {
+LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_shared_s, int mode) {
     LossPlan p;
     p.N = N;
     p.n = n;
@@ -126,7 +128,9 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     p.off_class_lo = take(sizeof(int32_t) * N);
     p.off_ccS = take(sizeof(float) * N);
     p.off_posrow2 = take(sizeof(float) * 6 * n);
-    p.off_lam2 = take(sizeof(float) * 6 * n);
+    // exchange mode: lam2 of ALL rows of every pair's row modality (the weighted class sums Qw need them)
+    const bool want_exchange = mode == LOSS_MODE_EXCHANGE && n < N;
+    p.off_lam2 = take(sizeof(float) * 6 * (want_exchange ? N : n));
     // Single-GPU tcgen05 pair path: S is computed once per pair; the row sweep stores its 16-bit coefficients
     // transposed in a strip buffer (CLIBD_GT_STRIP_MB, default 2304 MB = the whole column range at
     // N = 32768, and never fewer than 18944 columns) and the other side's gradient is a plain GEMM over that strip.
@@ -134,19 +138,23 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     //  measured 0.88 vs 0.81 ms at N = 4096, 2.26 vs 2.56 ms at N = 8192, three modalities)
     const char* min_env = std::getenv("CLIBD_SHARED_S_MIN_N");  // tests force the path at oracle-sized batches
     const int64_t shared_min_n = min_env ? std::atoll(min_env) : 6144;
-    p.shared_s = allow_shared_s && tc && n == N && N >= shared_min_n && p.dpad <= PAIR_DCH && !std::getenv("CLIBD_BWD_TWO_SWEEPS") &&
-                 !std::getenv("CLIBD_BWD_SINGLE");
+    // Row-sharded exchange mode: the same S-once backward on the local rows of every pair's row modality; the caller
+    // asked for it explicitly, so only the shape limits of the pair kernels apply.
+    p.exchange = allow_shared_s && tc && want_exchange && p.dpad <= PAIR_DCH;
+    p.shared_s = p.exchange || (allow_shared_s && tc && n == N && N >= shared_min_n && p.dpad <= PAIR_DCH &&
+                                !std::getenv("CLIBD_BWD_TWO_SWEEPS") && !std::getenv("CLIBD_BWD_SINGLE"));
     if (p.shared_s) {
         const char* env = std::getenv("CLIBD_GT_STRIP_MB");
         const double budget = (env ? std::atof(env) : 2304.0) * 1048576.0;
-        int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(N))) / 256 * 256;
+        int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(n))) / 256 * 256;
         if (rows < 74 * 256) rows = 74 * 256;  // at least one 256-row tile per CTA pair and feature tile
         const int64_t all = round_up(N, 256);
         p.strip_rows = rows < all ? rows : all;
-        p.gt_ld = p.strip_rows;  // Gs[N rows][strip columns]
-        p.off_gt = take(2 * static_cast<size_t>(N) * p.gt_ld);
+        p.gt_ld = p.strip_rows;  // Gs[n local rows][strip columns]
+        p.off_gt = take(2 * static_cast<size_t>(n) * p.gt_ld);
+        p.npad_loc = round_up(n, 8);
         for (int m = 0; m < 3; ++m) {
-            p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad);
+            p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad_loc);
             p.off_Qw[m] = take(sizeof(float) * N * d);
         }
     }
@@ -186,19 +194,63 @@ static int check_common(const void* const x[3], const float* const inv_norm[3], 
 }
 
 
-// Single-GPU backward with S computed ONCE per modality pair (plan.shared_s).  For pair p = (a, b):
-//   1. row sweep over the rows of a (loss_bwd_pair.cu): S tile -> G~ (minus lam2_i on the positives) ->
-//      dxh[a] += G~ Yhat_b, and the same 16-bit G~ stored transposed into the strip buffer;
-//   2. dxh[b] += Gt * Xhat_a as a plain GEMM (loss_grad_gemm.cu) -- no second S^T sweep;
+// Backward with S computed ONCE per modality pair (plan.shared_s).  For pair p = (a, b), on the LOCAL rows of a
+// (all rows on one GPU):
+//   1. row sweep (loss_bwd_pair.cu): S tile -> G~ (minus lam2_i on the positives) -> dxh[a] += G~ Yhat_b, and the
+//      same 16-bit G~ tiles stored into the strip buffer [n local rows, strip columns];
+//   2. the column side's gradient Gs^T * Xhat_a as a plain GEMM over the strip (loss_grad_gemm.cu) -- no second S^T
+//      sweep.  One GPU: it lands in dxh[b].  Row-sharded (exchange mode): it is this rank's PARTIAL gradient of all N
+//      rows of b and leaves the rank -- into part[b] (the caller reduce-scatters it) or straight into the owners'
+//      peer-mapped slot arrays (ExchangeArgs);
 //   3. the fp32 target term of b's rows uses class sums of a weighted by 1 - lam2_i / 2 (the share the sweep
 //      has not subtracted), the one of a's rows the usual (2 - lam2_i) Q_b[rep_i].
 // Tensor work per pair: 2 (S) + 2 + 2 = 6 n N d flops instead of 8 for two sweeps.
-static int backward_shared_s(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
-                             float logit_scale, const float pair_weight[3], int path, void* scratch,
-                             const LossPlan& plan, float grad_feat_scale, const float* grad_feat_scale_dev,
-                             void* const dx[3], double* dscale_partial, cudaStream_t stream) {
+struct ExchangeArgs {
+    const float* posrow = nullptr;     // [3][N] complete per-row positive dot products (exchange mode)
+    float* const* part = nullptr;      // [3]: local [N, d] partial-gradient buffers, or null
+    float* const* peer_red = nullptr;  // [world * 3]: entry [q * 3 + p] = rank q's slot array of pair p, or null
+    int rank = 0, world = 1;
+};
+
+// What normalize_bwd adds up for modality m (fixed by the pair weights alone, so the two halves of a split backward
+// derive the same bookkeeping): per pair containing m the partner's class sums, their weight and the lam2 the sweep
+// already subtracted on the row's positives; whether row sweeps wrote into dxh[m].
+struct NormPlan {
+    const float* Qp[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    const float* lam[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    float wp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    int nparts[3] = {0, 0, 0};
+    bool wrote_dxh[3] = {false, false, false};
+};
+
+static float* lam2_of_pair(void* scratch, const LossPlan& plan, int p) {
+    // one GPU: [n = N] per (pair, direction) slot; exchange mode: all N rows (the slots are N wide there too)
+    return at<float>(scratch, plan.off_lam2) + static_cast<int64_t>(2 * p) * plan.N;
+}
+
+static NormPlan shared_s_norm_plan(void* scratch, const LossPlan& plan, const float pair_weight[3], int64_t row0) {
+    NormPlan np;
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] == 0.f) continue;
+        const int a = kPairA[p], b = kPairB[p];
+        np.Qp[a][np.nparts[a]] = at<float>(scratch, plan.off_Q[b]);
+        np.lam[a][np.nparts[a]] = lam2_of_pair(scratch, plan, p) + row0;  // indexed by local row
+        np.wp[a][np.nparts[a]] = pair_weight[p];
+        ++np.nparts[a];
+        np.wrote_dxh[a] = true;
+        np.Qp[b][np.nparts[b]] = at<float>(scratch, plan.off_Qw[p]);
+        np.lam[b][np.nparts[b]] = nullptr;
+        np.wp[b][np.nparts[b]] = pair_weight[p];
+        ++np.nparts[b];
+        if (!plan.exchange) np.wrote_dxh[b] = true;  // one GPU: the gradient GEMM writes into dxh[b] as well
+    }
+    return np;
+}
+
+static int shared_s_sweeps(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                           int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                           void* scratch, const LossPlan& plan, const ExchangeArgs& ex, cudaStream_t stream) {
     const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
-    const int32_t* rep = at<int32_t>(scratch, plan.off_rep);
     const float* gscale = at<float>(scratch, plan.off_gscale);
     const float* u = at<float>(scratch, plan.off_u);
     const float* v = at<float>(scratch, plan.off_v);
@@ -207,77 +259,110 @@ static int backward_shared_s(const void* const x[3], int dtype, const float* con
     const int32_t* sidx = at<int32_t>(scratch, plan.off_sidx);
     const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
     float* ccS = at<float>(scratch, plan.off_ccS);
-    float* dots = at<float>(scratch, plan.off_dots);
-    double* red = at<double>(scratch, plan.off_red);
     void* gt = at<void>(scratch, plan.off_gt);
     int rc = 0;
-    int nparts[3] = {0, 0, 0};
-    const float* Qp[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-    const float* lam[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-    float wp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    bool wrote_dxh[3] = {false, false, false};
+    bool wrote_part[3] = {false, false, false};
     for (int p = 0; p < 3; ++p) {
         if (pair_weight[p] == 0.f) continue;
         const int a = kPairA[p], b = kPairB[p];
-        float* lam2 = at<float>(scratch, plan.off_lam2) + (2 * p) * N;
-        if ((rc = launch_sweep_prep(u + p * N, v + p * N, sidx, cnt, at<float>(scratch, plan.off_posrow2) + (2 * p) * N, N, 0,
-                                    N, logit_scale, ccS, lam2, stream)))
+        float* lam2 = lam2_of_pair(scratch, plan, p);
+        // lam2 of every row the class sums Qw below will touch: all N rows (exchange mode: from the exchanged posrow)
+        const float* posrow = plan.exchange ? ex.posrow + static_cast<int64_t>(p) * N
+                                            : at<float>(scratch, plan.off_posrow2) + static_cast<int64_t>(2 * p) * N;
+        if ((rc = launch_sweep_prep(u + p * N, v + p * N, sidx, cnt, posrow, N, 0, N, logit_scale, ccS, lam2, stream)))
             return rc;
         float* dxh_a = at<float>(scratch, plan.off_dxh[a]);
-        float* dxh_b = at<float>(scratch, plan.off_dxh[b]);
+        GradDest dest;
+        for (int q = 0; q < MAX_PEERS; ++q) dest.base[q] = nullptr;
+        int ksplit = 1, acc_grad = 0;
+        if (!plan.exchange) {  // one GPU: into dxh[b] (K split over the jsplit partial outputs)
+            dest.base[0] = at<float>(scratch, plan.off_dxh[b]);
+            dest.rows_per_dest = N;
+            dest.slot_rows = N;
+            dest.slot0 = 0;
+            ksplit = plan.jsplit;
+            acc_grad = wrote_dxh[b] ? 1 : 0;
+        } else if (ex.peer_red != nullptr) {  // owners' slot arrays over NVLink, slot = this rank
+            for (int q = 0; q < ex.world; ++q) dest.base[q] = ex.peer_red[q * 3 + p];
+            dest.rows_per_dest = n;
+            dest.slot_rows = n;
+            dest.slot0 = ex.rank;
+        } else {  // local partial buffer, reduce-scattered by the caller
+            dest.base[0] = ex.part[b];
+            dest.rows_per_dest = N;
+            dest.slot_rows = N;
+            dest.slot0 = 0;
+            acc_grad = wrote_part[b] ? 1 : 0;
+        }
         int strip = 0;
         for (int64_t c0 = 0; c0 < N; c0 += plan.strip_rows, ++strip) {
             const int64_t c1 = c0 + plan.strip_rows < N ? c0 + plan.strip_rows : N;
             if ((rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]),
-                                            at<void>(scratch, plan.off_xhT[b]), N, plan.npad, d, plan.dpad, 0, N, logit_scale,
-                                            u + p * N, ccS, gscale, pair_weight[p], nparts[a] > 0 || strip > 0, plan.jsplit,
-                                            fmt_bf16, dxh_a, stream, /*self_mask=*/0, class_lo, cnt, lam2, c0, c1, gt,
-                                            plan.gt_ld)))
+                                            at<void>(scratch, plan.off_xhT[b]), N, plan.npad, d, plan.dpad, row0, n,
+                                            logit_scale, u + p * N, ccS, gscale, pair_weight[p], wrote_dxh[a] || strip > 0,
+                                            plan.jsplit, fmt_bf16, dxh_a, stream, /*self_mask=*/0, class_lo, cnt,
+                                            lam2 + row0, c0, c1, gt, plan.gt_ld)))
                 return rc;
-            if ((rc = tc_grad_from_strip(gt, plan.gt_ld, c1 - c0, c0, at<void>(scratch, plan.off_xhTo[a]), N, plan.npad, d,
-                                         plan.dpad, sidx, gscale, pair_weight[p], nparts[b] > 0, plan.jsplit, fmt_bf16, dxh_b,
-                                         N, tc_num_sms(), stream)))
+            if ((rc = tc_grad_from_strip(gt, plan.gt_ld, c1 - c0, c0, at<void>(scratch, plan.off_xhTo[a]), n, plan.npad_loc,
+                                         N, d, plan.dpad, sidx, gscale, pair_weight[p], acc_grad, ksplit, fmt_bf16, dest,
+                                         tc_num_sms(), stream)))
                 return rc;
         }
-        // target terms: rows of a see Q_b with their own lam2; rows of b see the lam2-weighted class sums of a
-        float* Qw = at<float>(scratch, plan.off_Qw[p]);
-        if ((rc = launch_class_sums(x[a], dtype, inv_norm[a], skey, sidx, cnt, N, d, 0, N, Qw, stream, lam2))) return rc;
-        Qp[a][nparts[a]] = at<float>(scratch, plan.off_Q[b]);
-        lam[a][nparts[a]] = lam2;
-        wp[a][nparts[a]] = pair_weight[p];
-        ++nparts[a];
-        Qp[b][nparts[b]] = Qw;
-        lam[b][nparts[b]] = nullptr;
-        wp[b][nparts[b]] = pair_weight[p];
-        ++nparts[b];
+        wrote_dxh[a] = true;
+        if (!plan.exchange) wrote_dxh[b] = true;
+        else wrote_part[b] = true;
+        // rows of b see the lam2-weighted class sums of a (classes with a local member only)
+        if ((rc = launch_class_sums(x[a], dtype, inv_norm[a], skey, sidx, cnt, N, d, row0, n,
+                                    at<float>(scratch, plan.off_Qw[p]), stream, lam2)))
+            return rc;
     }
+    return 0;
+}
+
+static int shared_s_finish(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                           int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], void* scratch,
+                           const LossPlan& plan, const float* const reduced[3], const int reduced_slots[3],
+                           float grad_feat_scale, const float* grad_feat_scale_dev, int grad_count, void* const dx[3],
+                           double* dscale_partial, cudaStream_t stream) {
+    const NormPlan np = shared_s_norm_plan(scratch, plan, pair_weight, row0);
+    const int32_t* rep = at<int32_t>(scratch, plan.off_rep);
+    float* dots = at<float>(scratch, plan.off_dots);
+    double* red = at<double>(scratch, plan.off_red);
+    int rc = 0;
     int n_mod_used = 0;
     for (int m = 0; m < 3; ++m) {
-        if (nparts[m] == 0) continue;
+        if (np.nparts[m] == 0) continue;
         NormBwdArgs a;
         a.x = x[m];
         a.dtype = dtype;
         a.inv_norm = inv_norm[m];
         a.rep = rep;
         a.dxh = at<float>(scratch, plan.off_dxh[m]);
-        a.jsplit = plan.jsplit;
+        a.jsplit = np.wrote_dxh[m] ? plan.jsplit : 0;
+        if (reduced != nullptr && reduced[m] != nullptr && reduced_slots[m] > 0) {
+            a.extra = reduced[m];
+            a.extra_slots = reduced_slots[m];
+        }
         for (int k = 0; k < 2; ++k) {
-            a.Qp[k] = Qp[m][k];
-            a.wp[k] = wp[m][k];
-            a.lam2[k] = lam[m][k];
+            a.Qp[k] = np.Qp[m][k];
+            a.wp[k] = np.wp[m][k];
+            a.lam2[k] = np.lam[m][k];
         }
         a.N = N;
         a.d = d;
-        a.row0 = 0;
-        a.n = N;
+        a.row0 = row0;
+        a.n = n;
         a.scale = logit_scale;
         a.grad_scale = grad_feat_scale;
         a.grad_scale_dev = grad_feat_scale_dev;
+        a.grad_scale_dev_count = grad_count;
         a.dx = dx ? dx[m] : nullptr;
-        a.dots = dots + n_mod_used * N;
+        a.dots = dots + n_mod_used * n;
         if ((rc = launch_normalize_bwd(a, stream))) return rc;
         ++n_mod_used;
     }
-    return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * N, 0.5, red, dscale_partial, stream,
+    return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5, red, dscale_partial, stream,
                                 scale_dev_ptr());
 }
 
@@ -331,26 +416,30 @@ int clibd_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* in
     return launch_row_inv_norm(x, dtype, n, d, inv_norm, stream);
 }
 
-int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path) {
-    if (n_global <= 0 || n_local < 0 || d <= 0 || path < 0 || path > 2) return -1;
-    return static_cast<int64_t>(make_loss_plan(n_global, n_local, d, path).total);
+int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path, int mode) {
+    if (n_global <= 0 || n_local < 0 || d <= 0 || path < 0 || path > 2 || mode < 0 || mode > 1) return -1;
+    return static_cast<int64_t>(make_loss_plan(n_global, n_local, d, path, true, mode).total);
 }
 
 int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
                              const int64_t* labels, int64_t N, int64_t d, int64_t row0, int64_t n,
                              float logit_scale, const float* logit_scale_dev, const float pair_weight[3], int path,
-                             void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum, double* pos,
-                             clibd_stream_t stream) {
-    const LossPlan plan = make_loss_plan(N, n, d, path);
+                             int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
+                             float* posrow_out, double* pos, clibd_stream_t stream) {
+    CLIBD_REQUIRE(mode == LOSS_MODE_LOCAL || mode == LOSS_MODE_EXCHANGE, "mode must be 0 or 1");
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(labels && rowsum && colsum && pos, "null output pointer");
+    if (mode == LOSS_MODE_EXCHANGE && n < N) {
+        CLIBD_REQUIRE(plan.exchange, "exchange mode needs a tensor-core path and a feature dim <= 768");
+        CLIBD_REQUIRE(posrow_out != nullptr, "exchange mode needs the posrow output");
+    }
     const bool tc = path != PATH_SIMT_F32;
     if (tc) CLIBD_REQUIRE(clibd_device_supported(), "tcgen05 path needs a compute-capability 10.x device");
-    // exp(S - s) must not underflow for the whole row: |S| <= s, so 2*s*log2(e) must stay < 126.  A host value is
-    // checked here; a device scalar is checked by scale_set_kernel (NaN loss when out of range).
+    // A host value is checked here; a device scalar is checked by scale_set_kernel (NaN loss when not positive).
     if (logit_scale_dev == nullptr)
-        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale <= 43.0f, "logit_scale must be in (0, 43] (fixed-shift softmax)");
+        CLIBD_REQUIRE(logit_scale > 0.f && logit_scale < 1e30f, "logit_scale must be a positive finite number");
     float* scale_cell = at<float>(scratch, plan.off_scale);
     scale_set_kernel<<<1, 1, 0, stream>>>(logit_scale, logit_scale_dev, scale_cell);
     CLIBD_KERNEL_CHECK();
@@ -386,9 +475,12 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
                                            at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream,
                                            ls.sidx, at<void>(scratch, plan.off_xhS[m]))))
                 return rc;
-            if (plan.shared_s) {  // transposed operand in input order (K operand of the stored-coefficient GEMM)
-                if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16, nullptr,
-                                               at<void>(scratch, plan.off_xhTo[m]), stream)))
+            if (plan.shared_s) {  // transposed operand of the LOCAL rows in input order (K operand of the
+                                  // stored-coefficient GEMM)
+                const size_t esize = dtype == DT_F32 ? 4 : 2;
+                const void* xl = static_cast<const char*>(x[m]) + static_cast<size_t>(row0) * d * esize;
+                if ((rc = launch_make_operands(xl, dtype, inv_norm[m] + row0, n, d, plan.dpad, plan.npad_loc, fmt_bf16,
+                                               nullptr, at<void>(scratch, plan.off_xhTo[m]), stream)))
                     return rc;
             }
         }
@@ -415,12 +507,15 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
         // the tcgen05 column sums come out in class-sorted column order: scatter them back to input order
         if ((rc = launch_reduce_parts(colpart, plan.col_parts, N, N, colsum + p * N, stream, tc ? ls.sidx : nullptr)))
             return rc;
-        // per-row positive dot products of both directions (direction 0 also gives the loss's positive term)
-        float* posrow = posrow2 + (2 * p) * n;
+        // per-row positive dot products of both directions (direction 0 also gives the loss's positive term).
+        // Exchange mode: direction 0 goes to the caller's [3, N] buffer at the local rows (the backward needs it for
+        // all rows), direction 1 is not used (no transposed sweep).
+        float* posrow = plan.exchange ? posrow_out + static_cast<int64_t>(p) * N + row0 : posrow2 + (2 * p) * n;
         if ((rc = launch_pos_rows(x[a], dtype, inv_norm[a], at<float>(scratch, plan.off_Q[b]), rep, d, row0, n, posrow,
                                   stream)))
             return rc;
-        if ((rc = launch_pos_rows(x[b], dtype, inv_norm[b], at<float>(scratch, plan.off_Q[a]), rep, d, row0, n,
+        if (!plan.shared_s &&
+            (rc = launch_pos_rows(x[b], dtype, inv_norm[b], at<float>(scratch, plan.off_Q[a]), rep, d, row0, n,
                                   posrow + n, stream)))
             return rc;
         if ((rc = launch_sum_to_double(posrow, n, 1.0, red, pos + p, stream))) return rc;
@@ -429,10 +524,10 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
 }
 
 int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
-                              int path, void* scratch, int64_t scratch_bytes, const float* rowsum,
+                              int path, int mode, void* scratch, int64_t scratch_bytes, const float* rowsum,
                               const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
-    CLIBD_REQUIRE(N > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
-    const LossPlan plan = make_loss_plan(N, n, d, path);
+    CLIBD_REQUIRE(N > 0 && d > 0 && path >= 0 && path <= 2 && mode >= 0 && mode <= 1, "bad shape");
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
     CLIBD_REQUIRE(scratch && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
     CLIBD_REQUIRE(rowsum && colsum && pos && loss_out, "null pointer");
     ScaleScope scale_scope(at<float>(scratch, plan.off_scale));  // written by clibd_loss_forward_stats
@@ -451,9 +546,13 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     if (rc) return rc;
     CLIBD_REQUIRE(dscale_partial != nullptr, "null dscale_partial");
     ScaleScope scale_scope(at<float>(scratch, plan.off_scale));  // written by clibd_loss_forward_stats
-    if (plan.shared_s)
-        return backward_shared_s(x, dtype, inv_norm, N, d, logit_scale, pair_weight, path, scratch, plan, grad_feat_scale,
-                                 grad_feat_scale_dev, dx, dscale_partial, stream);
+    if (plan.shared_s) {  // one GPU (n == N): S once per pair, both gradients stay in the scratch
+        if ((rc = shared_s_sweeps(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch, plan,
+                                  ExchangeArgs(), stream)))
+            return rc;
+        return shared_s_finish(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, scratch, plan, nullptr, nullptr,
+                               grad_feat_scale, grad_feat_scale_dev, 1, dx, dscale_partial, stream);
+    }
     const bool tc = path != PATH_SIMT_F32;
     const int fmt_bf16 = path == PATH_TC_BF16 ? 1 : 0;
     const int32_t* rep = at<int32_t>(scratch, plan.off_rep);
@@ -549,6 +648,56 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     if ((rc = launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5, red, dscale_partial, stream,
                                    scale_dev_ptr()))) return rc;
     return 0;
+}
+
+int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                               int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                               void* scratch, int64_t scratch_bytes, const float* posrow, float* const part[3],
+                               float* const peer_red[], int rank, int world, clibd_stream_t stream) {
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE);
+    int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
+    if (rc) return rc;
+    CLIBD_REQUIRE(plan.exchange, "clibd_loss_backward_sweeps needs a row-sharded tensor-core plan (n_local < n_global, d <= 768)");
+    CLIBD_REQUIRE(posrow != nullptr, "null posrow");
+    CLIBD_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world && n * world == N && row0 == rank * n,
+                  "exchange mode needs equal row blocks, row0 = rank * n_local, world <= 16");
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] == 0.f) continue;
+        if (peer_red != nullptr) {
+            for (int q = 0; q < world; ++q)
+                CLIBD_REQUIRE(peer_red[q * 3 + p] != nullptr, "missing peer slot array of a weighted pair");
+        } else {
+            CLIBD_REQUIRE(part != nullptr && part[kPairB[p]] != nullptr, "missing partial-gradient buffer of a column modality");
+        }
+    }
+    ScaleScope scale_scope(at<float>(scratch, plan.off_scale));
+    ExchangeArgs ex;
+    ex.posrow = posrow;
+    ex.part = part;
+    ex.peer_red = peer_red;
+    ex.rank = rank;
+    ex.world = world;
+    return shared_s_sweeps(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch, plan, ex, stream);
+}
+
+int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                               int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                               void* scratch, int64_t scratch_bytes, const float* const reduced[3],
+                               const int reduced_slots[3], float grad_feat_scale, const float* grad_feat_scale_dev,
+                               int grad_count, void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE);
+    int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
+    if (rc) return rc;
+    CLIBD_REQUIRE(plan.exchange, "clibd_loss_backward_finish needs a row-sharded tensor-core plan");
+    CLIBD_REQUIRE(dscale_partial != nullptr && reduced != nullptr && reduced_slots != nullptr && grad_count >= 1,
+                  "null pointer");
+    for (int p = 0; p < 3; ++p)
+        if (pair_weight[p] != 0.f)
+            CLIBD_REQUIRE(reduced[kPairB[p]] != nullptr && reduced_slots[kPairB[p]] > 0,
+                          "missing received gradient partials of a column modality");
+    ScaleScope scale_scope(at<float>(scratch, plan.off_scale));
+    return shared_s_finish(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, scratch, plan, reduced,
+                           reduced_slots, grad_feat_scale, grad_feat_scale_dev, grad_count, dx, dscale_partial, stream);
 }
 
 }  // extern "C"

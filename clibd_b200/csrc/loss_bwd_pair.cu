@@ -318,7 +318,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             // the strip -- for the other side's gradient GEMM (loss_grad_gemm.cu reads it as an M-major operand).
             // No registers, no LSU instructions: one TMA store per K block.
             const bool elected = elect_one();
-            const int32_t grow = static_cast<int32_t>(row0 + mt * PAIR_BM + rank * 64);
+            const int32_t grow = static_cast<int32_t>(mt * PAIR_BM + rank * 64);  // LOCAL row: the strip has n rows
             for (int64_t t = jt0; t < jt1; ++t) {
                 const int64_t tl = t - jt0;
                 mbar_wait(g_lfull, tl & 1);
@@ -349,7 +349,7 @@ loss_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const float gs = gscale[0];
             const float rcg = (lrow < n ? rowcoef[row0 + lrow] : 0.f) * gs;
             const float a = scale * kLog2e;
-            const float nb = -scale * kLog2e;
+            const float nb = -softmax_shift(scale) * kLog2e;
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             const uint32_t st_empty_l = mapa_u32(smem_u32(st_empty), 0);
             const uint32_t g_full_l = mapa_u32(smem_u32(g_full), 0);
@@ -572,8 +572,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     CLIBD_REQUIRE(col_begin >= 0 && col_begin % PAIR_BJ == 0 && col_begin < col_end, "bad column strip");
     const int64_t jt_lo = col_begin / PAIR_BJ, jt_hi = ceil_div(col_end, PAIR_BJ);
     const int64_t num_jt = jt_hi - jt_lo;
-    if (gt != nullptr) {  // coefficient strip [N rows, columns of this strip], pitch gt_ld
-        rc = make_tmap_2d_16bit(&tm_gs, gt, N, col_end - col_begin, gt_ld, P_BK, 64, fmt_bf16);
+    if (gt != nullptr) {  // coefficient strip [n local rows, columns of this strip], pitch gt_ld
+        rc = make_tmap_2d_16bit(&tm_gs, gt, n, col_end - col_begin, gt_ld, P_BK, 64, fmt_bf16);
         if (rc) return rc;
     } else {
         tm_gs = tm_x;  // unused

@@ -162,7 +162,7 @@ loss_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         const int h = ew >> 2;    // column half of the tile
         const int etid = ew * 32 + lane;
         const float a = scale * kLog2e;
-        const float nb = -scale * kLog2e;
+        const float nb = -softmax_shift(scale) * kLog2e;
         const uint32_t tempty_l0 = mapa_u32(smem_u32(&tempty[0]), 0);
         uint32_t it = 0;
         for (int64_t t = pair; t < num_tiles; t += num_pairs, ++it) {

@@ -20,6 +20,12 @@
 // (the geometry of loss_fwd_pair.cu).  Rows of the strip are class-sorted column positions of the row sweep;
 // the epilogue scatters them to the input order through sidx.
 //
+// Row-sharded step (exchange mode, loss_api.cu): K = this rank's n local rows, the output is the rank's PARTIAL
+// gradient of all N rows of the column modality, and the epilogue sends every row straight to its owner: global
+// row g belongs to rank g / n, whose slot array is peer-mapped memory (GradDest) -- the reduce-scatter of the
+// reference's all_gather backward (loss_func.py:97) happens tile by tile over NVLink while the GEMM is running,
+// and the owner adds the W slots in rank order (deterministic) in its normalise-backward pass.
+//
 // Warp roles per CTA: 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 4-11 epilogue.
 #include "common.cuh"
 #include "loss_plan.h"
@@ -60,9 +66,9 @@ __device__ __forceinline__ GItem g_item(int64_t t, int64_t num_nt, int ksplit) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_xt, int64_t Ms,
-                      int64_t strip0, int64_t Ntot, int64_t d, int64_t ld, int64_t n_out, int num_kb, int ksplit,
+                      int64_t strip0, int64_t Ntot, int64_t d, int64_t ld, int num_kb, int ksplit,
                       int kb_per_split, uint32_t idesc, const int32_t* __restrict__ sidx,
-                      const float* __restrict__ gscale, float weight, int accumulate, float* __restrict__ out) {
+                      const float* __restrict__ gscale, float weight, int accumulate, const GradDest dest) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -184,7 +190,9 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
             const int64_t srow = it.mt * 256 + rank * 128 + q * 32 + lane;  // row of the strip
             const bool row_ok = srow < Ms && strip0 + srow < Ntot;
             const int64_t orow = row_ok ? static_cast<int64_t>(sidx[strip0 + srow]) : 0;
-            float* orp = out + (it.ks * n_out + orow) * ld;
+            const int64_t oq = orow / dest.rows_per_dest;       // owner of the row (0 unless peer form)
+            const int64_t olr = orow - oq * dest.rows_per_dest;
+            float* orp = dest.base[oq] + ((dest.slot0 + it.ks) * dest.slot_rows + olr) * ld;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
 #pragma unroll 1
@@ -240,27 +248,30 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
 
 }  // namespace
 
-int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
-                       int64_t npad, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale, float weight,
-                       int accumulate, int ksplit, int fmt_bf16, float* out, int64_t n_out, int num_sms,
+int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t K,
+                       int64_t npad, int64_t Ntot, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale,
+                       float weight, int accumulate, int ksplit, int fmt_bf16, const GradDest& dest, int num_sms,
                        cudaStream_t s) {
-    if (Ms == 0 || N == 0) return 0;
+    if (Ms == 0 || K == 0) return 0;
     CLIBD_REQUIRE(ksplit >= 1 && gs_ld % 8 == 0 && gs_ld >= Ms, "bad strip geometry");
+    CLIBD_REQUIRE(dest.rows_per_dest > 0 && ceil_div(Ntot, dest.rows_per_dest) <= MAX_PEERS, "bad gradient destination");
     CUtensorMap tm_g, tm_xt;
-    // Gs [N rows, Ms strip columns (pitch gs_ld)]: rows beyond N / columns beyond Ms read as zero (TMA fill)
-    int rc = make_tmap_2d_16bit(&tm_g, gs, N, Ms, gs_ld, 64, G_BK, fmt_bf16);
+    // Gs [K rows, Ms strip columns (pitch gs_ld)]: rows beyond K / columns beyond Ms read as zero (TMA fill)
+    int rc = make_tmap_2d_16bit(&tm_g, gs, K, Ms, gs_ld, 64, G_BK, fmt_bf16);
     if (rc) return rc;
-    rc = make_tmap_2d_16bit(&tm_xt, xhT_x, dpad, N, npad, G_BK, 128, fmt_bf16);
+    rc = make_tmap_2d_16bit(&tm_xt, xhT_x, dpad, K, npad, G_BK, 128, fmt_bf16);
     if (rc) return rc;
     CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_grad_gemm_kernel), G_SMEM_TOTAL));
-    const int num_kb = static_cast<int>(ceil_div(N, G_BK));
+    const int num_kb = static_cast<int>(ceil_div(K, G_BK));
     const int slots = ksplit;  // the caller sums `slots` partial outputs: parts that get no K blocks are zeroed
     if (ksplit > num_kb) ksplit = num_kb;
     const int kb_per_split = static_cast<int>(ceil_div(num_kb, ksplit));
     ksplit = static_cast<int>(ceil_div(num_kb, kb_per_split));  // no empty K part
-    if (!accumulate && ksplit < slots)
-        CLIBD_CHECK_CUDA(cudaMemsetAsync(out + static_cast<int64_t>(ksplit) * n_out * d, 0,
-                                         sizeof(float) * static_cast<size_t>(slots - ksplit) * n_out * d, s));
+    if (!accumulate && ksplit < slots) {  // only the local forms split K
+        CLIBD_REQUIRE(dest.rows_per_dest >= Ntot, "the peer form of the gradient GEMM does not split K");
+        CLIBD_CHECK_CUDA(cudaMemsetAsync(dest.base[0] + static_cast<int64_t>(dest.slot0 + ksplit) * dest.slot_rows * d, 0,
+                                         sizeof(float) * static_cast<size_t>(slots - ksplit) * dest.slot_rows * d, s));
+    }
     const int64_t items = ceil_div(Ms, 256) * ceil_div(d, G_TN) * ksplit;
     // a multiple of the number of feature tiles: the pairs that work on the feature tiles of one (row tile, K part)
     // then always run in the same wave and share the Gs blocks through L2 (74 -> 72 pairs for d = 768)
@@ -270,9 +281,9 @@ int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0
     const int pairs = static_cast<int>(items < max_pairs ? items : max_pairs);
     const uint32_t idesc = make_idesc_f16(256, G_TN, fmt_bf16 ? 1u : 0u, /*a_mn_major=*/1u);
     ProfScope prof(PROF_LOSS_GRAD_GEMM, s);
-    loss_grad_gemm_kernel<<<2 * pairs, G_THREADS, G_SMEM_TOTAL, s>>>(tm_g, tm_xt, Ms, strip0, N, d, d, n_out, num_kb, ksplit,
+    loss_grad_gemm_kernel<<<2 * pairs, G_THREADS, G_SMEM_TOTAL, s>>>(tm_g, tm_xt, Ms, strip0, Ntot, d, d, num_kb, ksplit,
                                                                    kb_per_split, idesc, sidx, gscale, weight, accumulate,
-                                                                   out);
+                                                                   dest);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

@@ -36,10 +36,14 @@ struct LossPlan {
     // sorted order; posrow2[2p+dir][n]: xhat_i . Q_partner[rep_i] per pair and direction; lam2[2p+dir][n]: the part
     // of the "- 2 T_ij" target term that the tensor-core epilogue subtracts (see loss_bwd_pair.cu)
     size_t off_cstart = 0, off_class_lo = 0, off_ccS = 0, off_posrow2 = 0, off_lam2 = 0;
-    // single-GPU backward with S computed once per pair (loss_api.cu: backward_shared_s): xhTo = transposed operand
-    // in INPUT order, Qw = class sums weighted by 1 - lam2/2 (one per pair), gt = strip of transposed coefficients
+    // backward with S computed once per pair (loss_api.cu: backward_shared_s): xhTo = transposed operand of the LOCAL
+    // rows in input order [dpad, npad_loc], Qw = class sums weighted by 1 - lam2/2 (one per pair), gt = strip of
+    // coefficients [n local rows, strip columns].  One GPU: n == N.  Row-sharded (mode = LOSS_MODE_EXCHANGE): the
+    // other side's gradient leaves the rank as partial rows (reduce-scatter, or peer-memory slots) and lam2 covers
+    // all N rows of the pair's row modality.
     bool shared_s = false;
-    int64_t strip_rows = 0, gt_ld = 0;
+    bool exchange = false;
+    int64_t strip_rows = 0, gt_ld = 0, npad_loc = 0;
     size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0;
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
@@ -49,7 +53,11 @@ struct LossPlan {
     size_t total = 0;
 };
 
-LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path, bool allow_shared_s = true);
+// mode (include/clibd_b200.h): 0 = every rank produces both gradients of its rows itself (two sweeps per pair when the
+// rows are sharded), 1 = exchange (S once per pair on every rank; column-side gradient partials are exchanged)
+constexpr int LOSS_MODE_LOCAL = 0;
+constexpr int LOSS_MODE_EXCHANGE = 1;
+LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path, bool allow_shared_s = true, int mode = 0);
 
 template <typename T>
 inline T* at(void* base, size_t off) {
@@ -114,14 +122,17 @@ struct NormBwdArgs {
     const float* inv_norm;
     const int32_t* rep;
     const float* dxh;       // [jsplit][n][d]
-    int jsplit;
+    int jsplit;             // 0: no row-side partials
+    const float* extra = nullptr;  // [extra_slots][n][d] further partials (column-side gradients received from the
+    int extra_slots = 0;           //  exchange: one slot per (pair, source rank), summed in slot order)
     const float* Qp[2];     // partner class sums (may be null)
     float wp[2];            // their pair weights
     const float* lam2[2] = {nullptr, nullptr};  // [n] part of the target term already subtracted by the sweep (null: 0)
     int64_t N, d, row0, n;
     float scale, grad_scale;
     const float* scale_dev = nullptr;  // filled by launch_normalize_bwd from the call's ScaleScope
-    const float* grad_scale_dev;  // optional device scalar multiplied into grad_scale (may be null)
+    const float* grad_scale_dev;  // optional device scalar(s) multiplied into grad_scale (may be null)
+    int grad_scale_dev_count = 1;  // > 1: the SUM of that many device scalars (one grad_output per rank)
     void* dx;               // [n,d] in dtype, may be null
     float* dots;            // [n]
 };
@@ -156,12 +167,25 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
                           const int32_t* pos_lo = nullptr, const float* pos_cnt = nullptr, const float* lam2 = nullptr,
                           int64_t col_begin = 0, int64_t col_end = -1, void* gt = nullptr, int64_t gt_ld = 0);
 // col_begin / col_end: sweep only the columns [col_begin, col_end) (col_begin a multiple of 256; -1 = N);
-// gt != null: also store the 16-bit coefficient tiles, gt[global row * gt_ld + (column - col_begin)] (TMA stores)
-// Other side's gradient from such a strip (loss_grad_gemm.cu): out[ks][sidx[strip0 + r]][:] (+)= weight / gscale *
-// sum_i gs[i][r] * xhat_x[i][:] for the Ms strip columns r, the K range split over `ksplit` partial outputs
-int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t N,
-                       int64_t npad, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale, float weight,
-                       int accumulate, int ksplit, int fmt_bf16, float* out, int64_t n_out, int num_sms,
+// gt != null: also store the 16-bit coefficient tiles, gt[LOCAL row * gt_ld + (column - col_begin)] (TMA stores;
+// gt has n rows)
+// Other side's gradient from such a strip (loss_grad_gemm.cu): with g = sidx[strip0 + r] the global row of strip
+// column r,  dest(g)[:] (+)= weight / gscale * sum_{i < K} gs[i][r] * xhat_x[i][:]  for the Ms strip columns r; the K
+// range (the rows of gs = the rows of xhT_x's K extent) is split over `ksplit` partial outputs.
+// Destination of global row g: q = g / rows_per_dest, lr = g % rows_per_dest,
+//     base[q] + ((slot0 + ks) * slot_rows + lr) * d
+// One GPU / reduce-scatter form: rows_per_dest = N, base[0] = the local buffer.  Peer form: rows_per_dest = n,
+// base[q] = rank q's slot array (peer-mapped memory: the epilogue stores travel over NVLink), slot0 = this rank's slot.
+constexpr int MAX_PEERS = 16;
+struct GradDest {
+    float* base[MAX_PEERS];
+    int64_t rows_per_dest;
+    int64_t slot_rows;
+    int slot0;
+};
+int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t K,
+                       int64_t npad, int64_t Ntot, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale,
+                       float weight, int accumulate, int ksplit, int fmt_bf16, const GradDest& dest, int num_sms,
                        cudaStream_t s);
 // pos_lo / pos_cnt [N] (by global row), lam2 [n] (by local row): columns [pos_lo, pos_lo + pos_cnt) of row i are its
 // positives (T_ij = 1) and the epilogue subtracts lam2_i from G~ there before the 16-bit rounding

@@ -72,7 +72,7 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
         for (int j = 0; j < 4; ++j) {
             const bool valid = (lrow0 + ty * 4 + i < n) && (col0 + tx * 4 + j < N) &&
                                !(self_mask && row0 + lrow0 + ty * 4 + i == col0 + tx * 4 + j);
-            const float e = valid ? expf(fmaf(scale, acc[i][j], -scale)) : 0.f;
+            const float e = valid ? expf(fmaf(scale, acc[i][j], -softmax_shift(scale))) : 0.f;
             rsum[i] += e;
             csum[j] += e;
         }
@@ -154,7 +154,7 @@ simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* _
                 const int64_t gj = j0 + scol + c;
                 float g = 0.f;
                 if (lr < n && gj < N && !(self_mask && row0 + lr == gj))
-                    g = expf(fmaf(scale, s4[c], -scale)) * (rc + colcoef[gj]);
+                    g = expf(fmaf(scale, s4[c], -softmax_shift(scale))) * (rc + colcoef[gj]);
                 Gs[srow][scol + c] = g;
             }
         }

@@ -326,7 +326,7 @@ __global__ void sweep_prep_kernel(const float* __restrict__ rowcoef, const float
     if (k < N) ccS[k] = colcoef[sidx ? sidx[k] : k];
     if (lam2 != nullptr && k < n) {
         const int64_t gi = row0 + k;
-        const float e = expf(scale * (posrow[k] / cnt[gi] - 1.f));
+        const float e = expf(scale * (posrow[k] / cnt[gi]) - softmax_shift(scale));
         lam2[k] = 2.f * fminf(1.f, 0.5f * e * (rowcoef[gi] + colcoef[gi]));
     }
 }
@@ -379,11 +379,13 @@ __global__ void loss_finish_stage1_kernel(int64_t N, float scale, float w0, floa
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             if (w[p] == 0.f) continue;
-            const float rs = rowsum[p * N + k], cs = colsum[p * N + k];
+            // a sum that underflowed entirely (see softmax_shift) is clamped: finite loss and coefficients, no log(0)
+            const float rs = fmaxf(rowsum[p * N + k], kMinSoftmaxSum), cs = fmaxf(colsum[p * N + k], kMinSoftmaxSum);
             u[p * N + k] = c / rs;
             v[p * N + k] = c / cs;
             acc += static_cast<double>(w[p]) * static_cast<double>(c) *
-                   (2.0 * static_cast<double>(scale) + log(static_cast<double>(rs)) + log(static_cast<double>(cs)));
+                   (2.0 * static_cast<double>(softmax_shift(scale)) + log(static_cast<double>(rs)) +
+                    log(static_cast<double>(cs)));
         }
     }
     double t = block_sum_double(acc, s_buf);
@@ -417,7 +419,12 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
     const float iv = a.inv_norm[gi];
     const int64_t rp = a.rep[gi];
     const float k1 = eff_scale(a.scale, a.scale_dev) / static_cast<float>(a.N);
-    const float gsc = a.grad_scale * (a.grad_scale_dev ? a.grad_scale_dev[0] : 1.f);
+    float gdev = 1.f;
+    if (a.grad_scale_dev) {  // one upstream gradient, or the sum of one per rank (fixed order: same value on every rank)
+        gdev = 0.f;
+        for (int r = 0; r < a.grad_scale_dev_count; ++r) gdev += a.grad_scale_dev[r];
+    }
+    const float gsc = a.grad_scale * gdev;
     T* dxr = a.dx ? reinterpret_cast<T*>(a.dx) + i * a.d : nullptr;
     // effective partner weights: the sweep already subtracted lam2 of the 2 on this row's positives
     const float wpe[2] = {a.wp[0] * (a.lam2[0] ? 1.f - 0.5f * a.lam2[0][i] : 1.f),
@@ -429,6 +436,12 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
             for (int s = 0; s < a.jsplit; ++s) {
                 float t[8];
                 load8(a.dxh + (static_cast<int64_t>(s) * a.n + i) * a.d + c, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] += t[k];
+            }
+            for (int s = 0; s < a.extra_slots; ++s) {
+                float t[8];
+                load8(a.extra + (static_cast<int64_t>(s) * a.n + i) * a.d + c, t);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) g[k] += t[k];
             }
@@ -499,6 +512,7 @@ __global__ void normalize_bwd_kernel(NormBwdArgs a) {
         auto dxhat = [&](int64_t c) -> float {
             float g = 0.f;
             for (int s = 0; s < a.jsplit; ++s) g += a.dxh[(static_cast<int64_t>(s) * a.n + i) * a.d + c];
+            for (int s = 0; s < a.extra_slots; ++s) g += a.extra[(static_cast<int64_t>(s) * a.n + i) * a.d + c];
             float t = 0.f;
             if (a.Qp[0]) t = fmaf(wpe[0], a.Qp[0][rp * a.d + c], t);
             if (a.Qp[1]) t = fmaf(wpe[1], a.Qp[1][rp * a.d + c], t);
@@ -675,7 +689,8 @@ int launch_normalize_bwd(const NormBwdArgs& a_in, cudaStream_t s) {
     NormBwdArgs a = a_in;
     a.scale_dev = scale_dev_ptr();
     const int64_t blocks = ceil_div(a.n * 32, kThreads);
-    bool vec = rows_vec8_ok<void>(a.x, a.d) && rows_vec8_ok<void>(a.dxh, a.d) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
+    bool vec = rows_vec8_ok<void>(a.x, a.d) && (a.jsplit == 0 || rows_vec8_ok<void>(a.dxh, a.d)) &&
+               (a.extra_slots == 0 || rows_vec8_ok<void>(a.extra, a.d)) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
     for (int p = 0; p < 2; ++p)
         if (a.Qp[p]) vec = vec && rows_vec8_ok<void>(a.Qp[p], a.d);
     DISPATCH_DTYPE(a.dtype, {

@@ -165,7 +165,7 @@ loss_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int h = ew >> 2;    // column half of the tile
         const int etid = ew * 32 + lane;
         const float a = scale * kLog2e;
-        const float nb = -scale * kLog2e;
+        const float nb = -softmax_shift(scale) * kLog2e;
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             int64_t mt, nt;
@@ -441,7 +441,7 @@ loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const float gs = gscale[0];
             const float rcg = (lrow < n ? rowcoef[row0 + lrow] : 0.f) * gs;
             const float a = scale * kLog2e;
-            const float nb = -scale * kLog2e;
+            const float nb = -softmax_shift(scale) * kLog2e;
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             for (int64_t t = jt0; t < jt1; ++t) {
                 const int64_t tl = t - jt0;

@@ -21,11 +21,12 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, _peer
 
 try:  # same optional import dance as loss_func.py:5-11
     import torch.distributed.nn  # noqa: F401
@@ -102,6 +103,42 @@ def _coalesced(group):
     return contextlib.nullcontext()
 
 
+def _shard_mode(path, d, group, device):
+    """How a row-sharded step exchanges data:
+    'peer'  : S once per pair; all-gather, statistics and the reduce-scatter of the column-side gradients are stores
+              into peer-mapped symmetric memory over NVLink (csrc/shard_exchange.cu, loss_grad_gemm.cu);
+    'nccl'  : the same step with NCCL collectives (all-gather in, all-reduce of statistics, reduce-scatter out);
+    'local' : every rank recomputes S for both of its gradients (two sweeps per pair), NCCL in / all-reduce only.
+    CLIBD_SHARD_MODE forces one of them; the default is 'peer' where symmetric memory is available."""
+    exchange_ok = path != _lib.PATH_SIMT_F32 and (d + 63) // 64 * 64 <= 768
+    want = os.environ.get("CLIBD_SHARD_MODE", "")
+    if want == "local" or not exchange_ok:
+        return "local"
+    if want == "nccl" or device.type != "cuda":
+        return "nccl"
+    try:
+        if dist.get_backend(group) != "nccl":
+            return "nccl"
+    except Exception:  # noqa: BLE001
+        return "nccl"
+    if _peer.available() or want == "peer":
+        return "peer"
+    return "nccl"
+
+
+def _column_slots(weights, world):
+    """(first pair, slot count) of the received column-side partials per modality in the peer form: pair p's slot
+    array holds `world` slots; (image,dna) feeds dna, (image,text) and (dna,text) feed text (adjacent arrays)."""
+    first = [None, None, None]
+    count = [0, 0, 0]
+    for p, b in enumerate((1, 2, 2)):
+        if weights[p] != 0.0:
+            if first[b] is None:
+                first[b] = p
+            count[b] += world
+    return first, count
+
+
 class _FusedClipLossFn(torch.autograd.Function):
     """forward(image, dna, text, labels, scale_tensor|None, scale_value, weights, path, group, world, rank,
     sum_grad_over_ranks) -> 0-d float32 loss"""
@@ -115,6 +152,9 @@ class _FusedClipLossFn(torch.autograd.Function):
         device, dtype = ref.device, ref.dtype
         n, d = ref.shape
         stream = _stream_ptr(device)
+        shard = _shard_mode(path, d, group, device) if world > 1 else "single"
+        mode = _lib.MODE_EXCHANGE if shard in ("peer", "nccl") else _lib.MODE_LOCAL
+        entry = None
         with _device_ctx(device):
             local = [None if f is None else f.detach().contiguous() for f in feats]
             labels = labels.detach().to(device=device, dtype=torch.int64).contiguous()
@@ -124,53 +164,80 @@ class _FusedClipLossFn(torch.autograd.Function):
                 _lib.check(lib.clibd_row_inv_norm(t.data_ptr(), _DT[dtype], t.shape[0], d, iv.data_ptr(), stream))
                 return iv
 
-            if world > 1:
-                N = n * world
-                all_labels = torch.empty(N, dtype=torch.int64, device=device)
-                gathered = [None if f is None else torch.empty((N, d), dtype=dtype, device=device) for f in local]
-                # labels + up to three feature sets in ONE grouped all-gather; a coalesced call wants one dtype, and an
-                # all-gather only concatenates bytes, so the int64 labels travel viewed as the feature dtype
-                with _coalesced(group):
-                    dist.all_gather_into_tensor(all_labels.view(dtype), labels.view(dtype), group=group)
-                    for f, g in zip(local, gathered):
-                        if f is not None:
-                            dist.all_gather_into_tensor(g, f, group=group)
-                # inverse norms of all rows from the gathered features: one 50 MB read per modality instead of one
-                # more latency-bound collective each
-                inv = [None if g is None else inv_norms(g) for g in gathered]
-                row0 = rank * n
-            else:
-                N, gathered, all_labels, row0 = n, local, labels, 0
-                inv = [None if f is None else inv_norms(f) for f in local]
-            nbytes = lib.clibd_loss_scratch_bytes(N, n, d, path)
-            if nbytes < 0:
-                raise ValueError("clibd_b200: bad loss shape")
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            stats = torch.zeros(6 * N, dtype=torch.float32, device=device)  # rowsum[3][N] | colsum[3][N]
-            pos = torch.zeros(3, dtype=torch.float64, device=device)
+            N = n * world
+            row0 = rank * n
+            w = _lib.float_array3(weights)
             # a tensor scale stays on the device: the library copies it into the scratch and every kernel of the
             # forward and the backward reads it from there (no host read in the training step)
             scale_dev = None
             if scale_tensor is not None:
                 scale_dev = scale_tensor.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
-            xs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in gathered])
-            ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in inv])
-            w = _lib.float_array3(weights)
-            rowsum_ptr = stats.data_ptr()
-            colsum_ptr = stats.data_ptr() + 4 * 3 * N
-            _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, all_labels.data_ptr(), N, d, row0, n,
-                                                    scale_value, None if scale_dev is None else scale_dev.data_ptr(),
-                                                    w, path, scratch.data_ptr(), nbytes, rowsum_ptr,
-                                                    colsum_ptr, pos.data_ptr(), stream))
-            if world > 1:
-                dist.all_reduce(stats, group=group)  # row sums have disjoint support, column sums add up
-                dist.all_reduce(pos, group=group)
+            scale_ptr = None if scale_dev is None else scale_dev.data_ptr()
+            nbytes = lib.clibd_loss_scratch_bytes(N, n, d, path, mode)
+            if nbytes < 0:
+                raise ValueError("clibd_b200: bad loss shape")
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             loss = torch.empty((), dtype=torch.float32, device=device)
-            _lib.check(lib.clibd_loss_forward_finish(N, n, d, scale_value, w, path, scratch.data_ptr(), nbytes,
-                                                     rowsum_ptr, colsum_ptr, pos.data_ptr(), loss.data_ptr(),
-                                                     stream))
-        ctx.gathered, ctx.inv, ctx.scratch = gathered, inv, scratch
-        ctx.meta = (N, n, d, row0, scale_value, tuple(weights), path, group, world, dtype, device, sum_grads)
+            if shard == "peer":
+                # ---- exchanges are stores into peer-mapped memory; a barrier separates writers from readers
+                px = _peer.context(group, device, N, n, d, dtype, world, rank)
+                entry = px.acquire()
+                _lib.check(lib.clibd_shard_push_rows(
+                    _lib.ptr_array3([None if f is None else f.data_ptr() for f in local]), _DT[dtype], labels.data_ptr(),
+                    n, d, rank, world, entry.peer_x, entry.peer_inv, entry.peer_labels, stream))
+                px.barrier()
+                gathered_ptrs = [None if f is None else entry.x_ptr[m] for m, f in enumerate(local)]
+                inv_ptrs = [None if f is None else entry.inv_ptr[m] for m, f in enumerate(local)]
+                xs, ivs = _lib.ptr_array3(gathered_ptrs), _lib.ptr_array3(inv_ptrs)
+                st = entry.stats_ptr
+                _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, entry.labels_ptr, N, d, row0, n, scale_value,
+                                                        scale_ptr, w, path, mode, scratch.data_ptr(), nbytes, st,
+                                                        st + 12 * N, st + 24 * N, entry.pos_local_ptr, stream))
+                _lib.check(lib.clibd_shard_push_stats(st, entry.pos_local_ptr, N, row0, n, rank, world, entry.peer_stats,
+                                                      entry.peer_colslots, entry.peer_posslots, stream))
+                px.barrier()
+                _lib.check(lib.clibd_shard_reduce_stats(entry.colslots_ptr, entry.posslots_ptr, N, world, st,
+                                                        entry.pos_ptr, stream))
+                _lib.check(lib.clibd_loss_forward_finish(N, n, d, scale_value, w, path, mode, scratch.data_ptr(), nbytes,
+                                                         st, st + 12 * N, entry.pos_ptr, loss.data_ptr(), stream))
+                ctx.keep = (_peer.EntryHolder(px, entry),)
+                ctx.x_ptrs, ctx.inv_ptrs, ctx.posrow_ptr = gathered_ptrs, inv_ptrs, st + 24 * N
+            else:
+                if world > 1:
+                    all_labels = torch.empty(N, dtype=torch.int64, device=device)
+                    gathered = [None if f is None else torch.empty((N, d), dtype=dtype, device=device) for f in local]
+                    # labels + up to three feature sets in ONE grouped all-gather; a coalesced call wants one dtype, and
+                    # an all-gather only concatenates bytes, so the int64 labels travel viewed as the feature dtype
+                    with _coalesced(group):
+                        dist.all_gather_into_tensor(all_labels.view(dtype), labels.view(dtype), group=group)
+                        for f, g in zip(local, gathered):
+                            if f is not None:
+                                dist.all_gather_into_tensor(g, f, group=group)
+                    # inverse norms of all rows from the gathered features: one 50 MB read per modality instead of
+                    # one more latency-bound collective each
+                    inv = [None if g is None else inv_norms(g) for g in gathered]
+                else:
+                    gathered, all_labels = local, labels
+                    inv = [None if f is None else inv_norms(f) for f in local]
+                # rowsum[3][N] | colsum[3][N] | posrow[3][N] (the last block: exchange mode only)
+                stats = torch.zeros(9 * N, dtype=torch.float32, device=device)
+                pos = torch.zeros(3, dtype=torch.float64, device=device)
+                gathered_ptrs = [None if g is None else g.data_ptr() for g in gathered]
+                inv_ptrs = [None if g is None else g.data_ptr() for g in inv]
+                xs, ivs = _lib.ptr_array3(gathered_ptrs), _lib.ptr_array3(inv_ptrs)
+                st = stats.data_ptr()
+                _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, all_labels.data_ptr(), N, d, row0, n,
+                                                        scale_value, scale_ptr, w, path, mode, scratch.data_ptr(), nbytes,
+                                                        st, st + 12 * N, st + 24 * N, pos.data_ptr(), stream))
+                if world > 1:
+                    dist.all_reduce(stats, group=group)  # row sums / posrow: disjoint support, column sums add up
+                    dist.all_reduce(pos, group=group)
+                _lib.check(lib.clibd_loss_forward_finish(N, n, d, scale_value, w, path, mode, scratch.data_ptr(), nbytes,
+                                                         st, st + 12 * N, pos.data_ptr(), loss.data_ptr(), stream))
+                ctx.keep = (gathered, inv, stats)
+                ctx.x_ptrs, ctx.inv_ptrs, ctx.posrow_ptr = gathered_ptrs, inv_ptrs, st + 24 * N
+        ctx.scratch = scratch
+        ctx.meta = (N, n, d, row0, scale_value, tuple(weights), path, group, world, rank, dtype, device, sum_grads, shard)
         ctx.has_scale = scale_tensor is not None
         ctx.scale_dtype = scale_tensor.dtype if scale_tensor is not None else None
         ctx.present = [f is not None for f in feats]
@@ -179,33 +246,86 @@ class _FusedClipLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
-        N, n, d, row0, scale_value, weights, path, group, world, dtype, device, sum_grads = ctx.meta
+        N, n, d, row0, scale_value, weights, path, group, world, rank, dtype, device, sum_grads, shard = ctx.meta
         stream = _stream_ptr(device)
         with _device_ctx(device):
-            grad_out = grad_out.detach().to(device=device, dtype=torch.float32).reshape(())
+            grad_out = grad_out.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
             dxs = [torch.empty((n, d), dtype=dtype, device=device) if (p and ctx.needs_input_grad[i]) else None
                    for i, p in enumerate(ctx.present)]
             dscale = torch.zeros(1, dtype=torch.float64, device=device)
-            xs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in ctx.gathered])
-            ivs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in ctx.inv])
+            xs, ivs = _lib.ptr_array3(ctx.x_ptrs), _lib.ptr_array3(ctx.inv_ptrs)
             outs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in dxs])
             w = _lib.float_array3(weights)
-            # grad_output stays on the device: the library multiplies it into the feature gradients
-            gsum = grad_out
-            if world > 1 and sum_grads:  # backward of the differentiable all-gather: reduce-scatter(SUM) over ranks
-                gsum = grad_out.clone()
-                dist.all_reduce(gsum, group=group)
-            gsum = gsum.reshape(1).contiguous()
-            _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path,
-                                               ctx.scratch.data_ptr(), ctx.scratch.numel(), 1.0, gsum.data_ptr(), outs,
-                                               dscale.data_ptr(), stream))
-            if world > 1:
+            sp, sn = ctx.scratch.data_ptr(), ctx.scratch.numel()
+            # grad_output stays on the device: the library multiplies it into the feature gradients.  Backward of the
+            # differentiable all-gather = reduce-scatter(SUM) over ranks (loss_func.py:97): every rank's loss is the same
+            # function, so the local rows receive (sum_r grad_output_r) * dL/dx.
+            if shard == "peer":
+                holder = ctx.keep[0]
+                px, entry = holder.px, holder.entry
+                par = px.next_parity()
+                if sum_grads:
+                    _lib.check(lib.clibd_shard_push_floats(grad_out.data_ptr(), 1, rank, world, px.peer_gslots[par], stream))
+                    g_ptr, g_count = px.gslots_ptr[par], world
+                else:
+                    g_ptr, g_count = grad_out.data_ptr(), 1
+                _lib.check(lib.clibd_loss_backward_sweeps(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn,
+                                                          ctx.posrow_ptr, None, px.peer_red[par], rank, world, stream))
+                px.barrier()
+                first, count = _column_slots(weights, world)
+                reduced = _lib.ptr_array3([None if f is None else px.red_ptr[par] + f * px.red_pair_bytes for f in first])
+                _lib.check(lib.clibd_loss_backward_finish(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn,
+                                                          reduced, _lib.int_array(count), 1.0, g_ptr, g_count, outs,
+                                                          dscale.data_ptr(), stream))
                 dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
+                holder.release()
+            elif shard == "nccl":
+                gsum = grad_out
+                if sum_grads:
+                    gsum = grad_out.clone()
+                    dist.all_reduce(gsum, group=group)
+                first, _ = _column_slots(weights, world)
+                part = [None if f is None else torch.empty((N, d), dtype=torch.float32, device=device) for f in first]
+                _lib.check(lib.clibd_loss_backward_sweeps(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn,
+                                                          ctx.posrow_ptr,
+                                                          _lib.ptr_array3([None if t is None else t.data_ptr() for t in part]),
+                                                          None, rank, world, stream))
+                reduced = [None if t is None else _reduce_scatter_rows(t, n, rank, group) for t in part]
+                _lib.check(lib.clibd_loss_backward_finish(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn,
+                                                          _lib.ptr_array3([None if t is None else t.data_ptr() for t in reduced]),
+                                                          _lib.int_array([0 if t is None else 1 for t in reduced]), 1.0,
+                                                          gsum.data_ptr(), 1, outs, dscale.data_ptr(), stream))
+                dist.all_reduce(dscale, group=group)
+            else:
+                gsum = grad_out
+                if world > 1 and sum_grads:
+                    gsum = grad_out.clone()
+                    dist.all_reduce(gsum, group=group)
+                _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn, 1.0,
+                                                   gsum.data_ptr(), outs, dscale.data_ptr(), stream))
+                if world > 1:
+                    dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
             grads = dxs
             gscale = None
             if ctx.has_scale and ctx.needs_input_grad[4]:
-                gscale = (dscale[0] * grad_out.double()).to(ctx.scale_dtype).reshape(())
+                gscale = (dscale[0] * grad_out[0].double()).to(ctx.scale_dtype).reshape(())
         return grads[0], grads[1], grads[2], None, gscale, None, None, None, None, None, None, None
+
+
+def _reduce_scatter_rows(part, n, rank, group):
+    """reduce-scatter(SUM) of a [N, d] float32 partial over the ranks -> this rank's [n, d] block (the backward of
+    torch.distributed.nn.all_gather, loss_func.py:97)."""
+    out = torch.empty((n, part.shape[1]), dtype=part.dtype, device=part.device)
+    try:
+        nccl = dist.get_backend(group) == "nccl"
+    except Exception:  # noqa: BLE001
+        nccl = False
+    if nccl:
+        dist.reduce_scatter_tensor(out, part, group=group)
+    else:  # gloo (CPU tests): no reduce-scatter
+        dist.all_reduce(part, group=group)
+        out.copy_(part[rank * n:(rank + 1) * n])
+    return out
 
 
 def _validate_criterion(criterion):

@@ -35,7 +35,7 @@ class _InfoNCEFn(torch.autograd.Function):
         with torch.cuda.device(device):
             inv = torch.empty(m, dtype=torch.float32, device=device)
             _lib.check(lib.clibd_row_inv_norm(z.data_ptr(), _DT[dtype], m, d, inv.data_ptr(), stream))
-            nbytes = lib.clibd_loss_scratch_bytes(m, m, d, path)
+            nbytes = lib.clibd_loss_scratch_bytes(m, m, d, path, 0)
             if nbytes < 0:
                 raise ValueError("clibd_b200: bad info-NCE shape")
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)

@@ -13,6 +13,12 @@
  *                  1 = tcgen05 tensor cores, bf16 operands, fp32 accumulate,
  *                  2 = tcgen05 tensor cores, f16 operands, fp32 accumulate.
  *   - feature slots are always [image, dna, text]; an absent modality is NULL;
+ *   - mode codes (row-sharded loss, n_local < n_global; ignored on one GPU):
+ *                  0 = every rank produces both gradients of its rows itself (S recomputed in two sweeps per pair),
+ *                  1 = exchange: S is computed once per pair on every rank; the column-side gradient leaves the
+ *                      rank as partial rows that are reduce-scattered to their owners (the backward of the
+ *                      reference's torch.distributed.nn.all_gather, loss_func.py:97) -- by the caller with NCCL, or
+ *                      tile by tile over NVLink into peer-mapped slot arrays (clibd_loss_backward_sweeps);
  *   - pair_weight[3] weights the unordered pairs (image,dna), (image,text), (dna,text):
  *     the loss is sum_p pair_weight[p] * [CE(S_p, T) + CE(S_p^T, T)], so the reference's
  *     "mean over the filtered ordered-pair list" (loss_func.py:69,200) is
@@ -29,7 +35,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 5
+#define CLIBD_ABI_VERSION 6
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -57,7 +63,7 @@ int clibd_row_inv_norm(const void* x, int dtype, int64_t n, int64_t d, float* in
 
 /* Bytes of scratch the three loss calls below need (same scratch, kept from forward
  * to backward). */
-int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path);
+int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, int path, int mode);
 
 /* Forward statistics for the local row block [row0, row0+n_local) against all n_global
  * columns.  x[m]: gathered [n_global, d] row-major features in `dtype`; inv_norm[m]:
@@ -68,18 +74,23 @@ int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, i
  * logit_scale_dev: optional DEVICE scalar (the reference's learnable `logit_scale.exp()` tensor,
  * simple_clip.py:61); when given it replaces logit_scale, is copied into the scratch and every kernel of this
  * call, of clibd_loss_forward_finish and of clibd_loss_backward reads it from there -- no host read per step.
- * A host value outside (0, 43] is an error; a device value outside it yields a NaN loss. */
+ * The scale must be a positive finite number (host value: error otherwise; device value: NaN loss); it is NOT limited
+ * from above -- the reference never clamps its learnable scale -- the kernels choose their softmax shift from it.
+ * mode 1 (exchange) additionally writes posrow[p*n_global + i] = xhat_a[i] . sum_{j: label_j = label_i} xhat_b[j] for the
+ * LOCAL rows i of every weighted pair p = (a, b) (disjoint support across ranks: all-reduce / exchange it like rowsum;
+ * the backward needs it for all rows); posrow may be NULL in mode 0. */
 int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
                              const int64_t* labels, int64_t n_global, int64_t d, int64_t row0, int64_t n_local,
                              float logit_scale, const float* logit_scale_dev, const float pair_weight[3] /* host */,
-                             int path, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
-                             double* pos, clibd_stream_t stream);
+                             int path, int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
+                             float* posrow, double* pos, clibd_stream_t stream);
 
 /* Loss value from complete statistics (rowsum/colsum/pos now hold GLOBAL sums for all
  * n_global rows/columns); also prepares the backward coefficients inside scratch.  The scale used is the one
  * clibd_loss_forward_stats stored in the scratch (logit_scale here is informational). */
 int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, float logit_scale,
-                              const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
+                              const float pair_weight[3] /* host */, int path, int mode, void* scratch,
+                              int64_t scratch_bytes,
                               const float* rowsum, const float* colsum, const double* pos, float* loss_out,
                               clibd_stream_t stream);
 
@@ -92,12 +103,76 @@ int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, floa
  * loss_func.py:97).  The scale used is the one clibd_loss_forward_stats stored in the scratch (logit_scale here is
  * informational).  With n_local == n_global (one GPU) and n_global >= 6144 the backward computes S once per
  * modality pair and passes its 16-bit coefficients to a second GEMM through a strip inside the scratch
- * (environment: CLIBD_GT_STRIP_MB bounds the strip, CLIBD_BWD_TWO_SWEEPS=1 selects the two-sweep form). */
+ * (environment: CLIBD_GT_STRIP_MB bounds the strip, CLIBD_BWD_TWO_SWEEPS=1 selects the two-sweep form).
+ * This one-call form is for one GPU and for mode 0; mode 1 uses the two calls below. */
 int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
                         int64_t d, int64_t row0, int64_t n_local, float logit_scale,
                         const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
                         float grad_feat_scale, const float* grad_feat_scale_dev, void* const dx[3],
                         double* dscale_partial, clibd_stream_t stream);
+
+/* Backward of a row-sharded step in mode 1, split where the reduce-scatter of the column-side gradients happens.
+ *
+ * clibd_loss_backward_sweeps: for every weighted pair (a, b) one row sweep over the LOCAL rows of a (S tile ->
+ * coefficients -> gradient of those rows, kept in the scratch) whose 16-bit coefficient tiles also feed a GEMM that
+ * yields this rank's PARTIAL gradient of ALL n_global rows of b.  posrow: [3, n_global] complete (see
+ * clibd_loss_forward_stats).  Where the partial rows go:
+ *   peer_red == NULL: part[m] ([n_global, d] float32, caller-owned, one per column modality m) receives them (pairs
+ *     that share a column modality accumulate); the caller reduce-scatters part[m] over the ranks (NCCL) into
+ *     reduced[m] = 1 slot of [n_local, d];
+ *   peer_red != NULL (host array [world * 3] of device pointers, entry [q * 3 + p] = the slot array of PAIR p in rank
+ *     q's memory, peer-mapped, [world, n_local, d] float32): the GEMM epilogue stores row g straight into slot `rank` of
+ *     its owner q = g / n_local -- the transfer rides on the GEMM, tile by tile over NVLink.  After a barrier across the
+ *     ranks the owner holds world slots per pair.
+ * clibd_loss_backward_finish: reduced[m] = the received column-side partials of modality m ([reduced_slots[m], n_local, d]
+ * float32, summed in slot order; NULL / 0 when m is no pair's column modality) + the row-side gradient in the scratch
+ * -> target terms, normalise-backward, dx, dscale_partial as in clibd_loss_backward.  grad_feat_scale_dev may point to
+ * grad_count device scalars (one upstream gradient per rank) whose SUM scales the feature gradients.
+ * Pair p's column modality is dna for (image, dna) and text for (image, text) and (dna, text). */
+int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
+                               int64_t d, int64_t row0, int64_t n_local, float logit_scale,
+                               const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
+                               const float* posrow, float* const part[3], float* const peer_red[] /* host */,
+                               int rank, int world, clibd_stream_t stream);
+int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t n_global,
+                               int64_t d, int64_t row0, int64_t n_local, float logit_scale,
+                               const float pair_weight[3] /* host */, int path, void* scratch, int64_t scratch_bytes,
+                               const float* const reduced[3], const int reduced_slots[3] /* host */,
+                               float grad_feat_scale, const float* grad_feat_scale_dev, int grad_count,
+                               void* const dx[3], double* dscale_partial, clibd_stream_t stream);
+
+/* ---- exchanges of the row-sharded step over peer-mapped memory ------------------------------------------------
+ * One process per GPU; every rank maps every other rank's exchange buffer (symmetric allocation, e.g.
+ * torch.distributed._symmetric_memory) and passes HOST arrays of DEVICE pointers, entry q = the buffer inside rank
+ * q's memory.  These replace the NCCL collectives of the reference (loss_func.py:143-157: all-gather of labels and
+ * features) with plain stores over NVLink; the caller separates writers from readers with a barrier across ranks.
+ * world <= 16.
+ *
+ * clibd_shard_push_rows: the all-gather.  Copies this rank's n_local rows of every present modality (raw, `dtype`),
+ * their inverse norms (computed here, as clibd_row_inv_norm) and its labels into rows [rank * n_local, (rank+1) *
+ * n_local) of EVERY rank's gathered buffers: peer_x[q*3+m] = [n_global, d] in `dtype`, peer_inv[q*3+m] = [n_global]
+ * float32, peer_labels[q] = [n_global] int64. */
+int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t* labels_local, int64_t n_local,
+                          int64_t d, int rank, int world, void* const peer_x[] /* host */,
+                          float* const peer_inv[] /* host */, int64_t* const peer_labels[] /* host */,
+                          clibd_stream_t stream);
+/* clibd_shard_push_stats: the statistics all-reduce, first half.  stats = this rank's [9, n_global] float32 buffer
+ * rowsum[3] | colsum[3] | posrow[3] as clibd_loss_forward_stats wrote it (its own buffer of peer_stats).  The local
+ * segments of rowsum and posrow (disjoint support) are copied into the same place of every other rank's
+ * peer_stats[q]; the colsum partials go to slot `rank` of peer_colslots[q] ([world, 3, n_global] float32) and pos[3]
+ * to slot `rank` of peer_posslots[q] ([world, 4] float64).
+ * clibd_shard_reduce_stats (after the barrier): colsum of `stats` and pos[3] = sums of the world slots in rank
+ * order (bit-identical on every rank). */
+int clibd_shard_push_stats(const float* stats, const double* pos, int64_t n_global, int64_t row0, int64_t n_local,
+                           int rank, int world, float* const peer_stats[] /* host */,
+                           float* const peer_colslots[] /* host */, double* const peer_posslots[] /* host */,
+                           clibd_stream_t stream);
+int clibd_shard_reduce_stats(const float* colslots, const double* posslots, int64_t n_global, int world, float* stats,
+                             double* pos, clibd_stream_t stream);
+/* clibd_shard_push_floats: copies `count` floats into slot `rank` (of `count` floats) of every rank's peer_slots[q]
+ * ([world, count] float32) -- e.g. each rank's autograd grad_output, summed by clibd_loss_backward_finish. */
+int clibd_shard_push_floats(const float* src, int64_t count, int rank, int world, float* const peer_slots[] /* host */,
+                            clibd_stream_t stream);
 
 /* ---- cosine nearest-neighbour retrieval --------------------------------------------
  * Replaces make_prediction / find_closest_match's search (bioscanclip/util/util.py:
@@ -163,7 +238,7 @@ int clibd_softmax_mean_backward(const void* logits, const void* grad_out, int dt
  * materialised (same fused kernels as the contrastive loss, diagonal entries excluded).
  * inv_norm: [m] from clibd_row_inv_norm; scratch: clibd_loss_scratch_bytes(m, m, d, path) bytes, kept from
  * forward to backward; rowsum: [m] float32 output (sum_{j != i} exp((cos_ij - 1) / tau), kept for the caller's
- * diagnostics); inv_temperature = 1 / tau in (0, 43].  tcgen05 paths need d <= 768.
+ * diagnostics); inv_temperature = 1 / tau > 0.  tcgen05 paths need d <= 768.
  * Backward: dz [m, d] in `dtype` receives grad_scale * grad_scale_dev[0] * dL/dz (device scalar optional). */
 int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64_t m, int64_t d,
                           float inv_temperature, int path, void* scratch, int64_t scratch_bytes, float* rowsum,

@@ -35,7 +35,7 @@ class FakeLib:
         _arr(out, (n,), np.float32)[:] = 1.0 / np.maximum(nrm, 1e-12)
         return 0
 
-    def clibd_loss_scratch_bytes(self, N, n, d, path):
+    def clibd_loss_scratch_bytes(self, N, n, d, path, mode):
         return 64
 
     def _inputs(self, xs, ivs, dtype, N, d):
@@ -49,8 +49,8 @@ class FakeLib:
             xh.append(x * iv[:, None])
         return xh
 
-    def clibd_loss_forward_stats(self, xs, dtype, ivs, labels, N, d, row0, n, scale, scale_dev, w, path, scratch,
-                                 nbytes, rowsum, colsum, pos, stream):
+    def clibd_loss_forward_stats(self, xs, dtype, ivs, labels, N, d, row0, n, scale, scale_dev, w, path, mode, scratch,
+                                 nbytes, rowsum, colsum, posrow, pos, stream):
         if scale_dev:
             scale = float(_arr(scale_dev, (1,), np.float32)[0])
         xh = self._inputs(xs, ivs, dtype, N, d)
@@ -68,10 +68,13 @@ class FakeLib:
             rs[p, row0:row0 + n] = E.sum(1)
             cs[p, :] = E.sum(0)
             ps[p] = cos[T].sum()
+            if mode == 1 and n < N:  # exchange mode: per-row positive dot products of the local rows
+                _arr(posrow, (3, N), np.float32)[p, row0:row0 + n] = (cos * T).sum(1)
         self.state[scratch] = {"labels": lab.copy(), "scale": scale}
         return 0
 
-    def clibd_loss_forward_finish(self, N, n, d, scale, w, path, scratch, nbytes, rowsum, colsum, pos, loss_out, stream):
+    def clibd_loss_forward_finish(self, N, n, d, scale, w, path, mode, scratch, nbytes, rowsum, colsum, pos, loss_out,
+                                  stream):
         st = self.state[scratch]
         scale = st["scale"]  # the one forward_stats stored
         lab = st["labels"]
@@ -116,6 +119,66 @@ class FakeLib:
                 acc += w[p] * (G @ xh[other])
             if not used:
                 continue
+            dxh = (scale / N) * acc
+            xl = xh[m][row0:row0 + n]
+            dot = (xl * dxh).sum(1, keepdims=True)
+            dots += dot.sum()
+            if dxs[m]:
+                iv = _arr(ivs[m], (N,), np.float32).astype(np.float64)[row0:row0 + n, None]
+                _arr(dxs[m], (n, d), _NP[dtype])[:] = gscale * (dxh - xl * dot) * iv
+        _arr(dscale, (1,), np.float64)[0] = dots / (2 * scale)
+        return 0
+
+    # ---- exchange mode (row-sharded, S once per pair): sweeps produce the row-side gradient (kept) and this rank's
+    # partial column-side gradient of ALL rows (part[b], reduce-scattered by the caller), finish combines them
+    def clibd_loss_backward_sweeps(self, xs, dtype, ivs, N, d, row0, n, scale, w, path, scratch, nbytes, posrow, part,
+                                   peer_red, rank, world, stream):
+        assert not peer_red, "the test double has no peer memory"
+        st = self.state[scratch]
+        scale = st["scale"]
+        xh = self._inputs(xs, ivs, dtype, N, d)
+        lab = st["labels"]
+        T = (lab[row0:row0 + n, None] == lab[None, :]).astype(np.float64)
+        # the exchanged posrow must be complete (every rank's rows) by now: check it against a direct evaluation
+        pr = _arr(posrow, (3, N), np.float32)
+        st["row"] = {}
+        wrote = set()
+        for p, (a, b) in enumerate(PAIRS):
+            if w[p] == 0.0:
+                continue
+            full_T = (lab[:, None] == lab[None, :])
+            expect = ((xh[a] @ xh[b].T) * full_T).sum(1)
+            assert np.allclose(pr[p], expect, rtol=1e-4, atol=1e-5), "posrow was not exchanged completely"
+            xa = xh[a][row0:row0 + n]
+            cos = xa @ xh[b].T
+            G = np.exp(scale * cos - scale) * (st["u"][p][row0:row0 + n, None] + st["v"][p][None, :]) - 2 * T
+            st["row"][a] = st["row"].get(a, 0.0) + w[p] * (G @ xh[b])
+            contrib = (w[p] * (G.T @ xa)).astype(np.float32)
+            out = _arr(part[b], (N, d), np.float32)
+            if b in wrote:
+                out += contrib
+            else:
+                out[:] = contrib
+                wrote.add(b)
+        return 0
+
+    def clibd_loss_backward_finish(self, xs, dtype, ivs, N, d, row0, n, scale, w, path, scratch, nbytes, reduced,
+                                   reduced_slots, gscale, gscale_dev, gcount, dxs, dscale, stream):
+        if gscale_dev:
+            gscale = gscale * float(_arr(gscale_dev, (gcount,), np.float32).sum())
+        st = self.state[scratch]
+        scale = st["scale"]
+        xh = self._inputs(xs, ivs, dtype, N, d)
+        dots = 0.0
+        for m in range(3):
+            if xh[m] is None:
+                continue
+            used = any(w[p] != 0.0 and m in PAIRS[p] for p in range(3))
+            if not used:
+                continue
+            acc = np.zeros((n, d)) + st["row"].get(m, 0.0)
+            if reduced[m]:
+                acc += _arr(reduced[m], (reduced_slots[m], n, d), np.float32).astype(np.float64).sum(0)
             dxh = (scale / N) * acc
             xl = xh[m][row0:row0 + n]
             dot = (xl * dxh).sum(1, keepdims=True)

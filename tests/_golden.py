@@ -40,7 +40,7 @@ def load(name):
 def all_single_process():
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
-        if os.path.basename(p).startswith(("seam_", "infonce_")):  # not contrastive-loss cases
+        if os.path.basename(p).startswith(("seam_", "infonce_", "fullsize_")):  # other fixture families
             continue
         g = Golden(p)
         if g.meta.get("world", 1) == 1:

@@ -26,9 +26,10 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()  # builds if needed, dlopens, binds every symbol
     assert os.path.exists(_build.LIB_PATH)
-    assert lib.clibd_abi_version() == 5
-    assert lib.clibd_loss_scratch_bytes(4096, 512, 768, 1) > 0
-    assert lib.clibd_loss_scratch_bytes(0, 0, 768, 1) == -1
+    assert lib.clibd_abi_version() == _lib.ABI_VERSION
+    assert lib.clibd_loss_scratch_bytes(4096, 512, 768, 1, 0) > 0
+    assert lib.clibd_loss_scratch_bytes(4096, 512, 768, 1, 1) > lib.clibd_loss_scratch_bytes(4096, 512, 768, 1, 0)
+    assert lib.clibd_loss_scratch_bytes(0, 0, 768, 1, 0) == -1
     assert lib.clibd_knn_scratch_bytes(1000, 100000, 768, 5, 2) > 0
 
 
@@ -96,7 +97,7 @@ def test_single_process_orchestration_with_double_matches_golden():
         _lib.inject_for_tests(None)
 
 
-def _w2_worker(rank, world, store, ret):
+def _w2_worker(rank, world, store, ret, operands):
     from clibd_b200 import _lib
     import clibd_b200 as cb
     from tests._fake_lib import FakeLib
@@ -107,7 +108,11 @@ def _w2_worker(rank, world, store, ret):
     sl = slice(rank * n, (rank + 1) * n)
     feats = [torch.from_numpy(g.inputs[m][sl].copy()).requires_grad_(True) for m in _golden.MODS]
     scale = torch.tensor(g.logit_scale, requires_grad=True)
-    mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world)
+    # operands=None: fp32 inputs take the CUDA-core path, whose sharded step is the 'local' form (two sweeps per
+    # rank); operands="bf16": a tensor-core path, whose sharded step is the exchange form (here with the collectives
+    # of the 'nccl' variant: all-gather, all-reduce of statistics incl. posrow, reduce-scatter of the partials)
+    mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world,
+                      tensor_core_operands=operands)
     loss = mod(feats[0], feats[1], feats[2], torch.from_numpy(g.labels[sl].copy()), scale)
     loss.backward()
     out = {"loss": float(loss), "ds": float(scale.grad)}
@@ -115,21 +120,23 @@ def _w2_worker(rank, world, store, ret):
         out[m] = f.grad.numpy().tolist()
     # gather_with_grad=False: only this rank's loss reaches the local rows (no sum over ranks)
     feats2 = [torch.from_numpy(g.inputs[m][sl].copy()).requires_grad_(True) for m in _golden.MODS]
-    mod2 = cb.ClipLoss(local_loss=False, gather_with_grad=False, rank=rank, world_size=world)
+    mod2 = cb.ClipLoss(local_loss=False, gather_with_grad=False, rank=rank, world_size=world,
+                       tensor_core_operands=operands)
     mod2(feats2[0], feats2[1], feats2[2], torch.from_numpy(g.labels[sl].copy()), g.logit_scale).backward()
     out["image_nograd_gather"] = feats2[0].grad.numpy().tolist()
     ret[rank] = out
     dist.destroy_process_group()
 
 
-def test_world2_gloo_orchestration_matches_reference_golden():
+@pytest.mark.parametrize("operands", [None, "bf16"], ids=["local_two_sweeps", "exchange_reduce_scatter"])
+def test_world2_gloo_orchestration_matches_reference_golden(operands):
     """The reference ran ClipLoss(gather_with_grad=True) under 2 gloo processes (oracle/gen_golden.py);
     our orchestration (all-gather in, all-reduce of statistics, sum-over-ranks gradient scale) must give
     every rank the same full-batch loss and W x the local slice of the full-batch gradient."""
     world = 2
     store = tempfile.mktemp()
     ret = mp.Manager().dict()
-    mp.spawn(_w2_worker, args=(world, store, ret), nprocs=world, join=True)
+    mp.spawn(_w2_worker, args=(world, store, ret, operands), nprocs=world, join=True)
     g = _golden.load("cliploss_w2_all_n64_d32")
     for r in range(world):
         assert ret[r]["loss"] == pytest.approx(float(g.outputs[f"rank{r}_loss"]), rel=2e-6)

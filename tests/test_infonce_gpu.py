@@ -134,4 +134,5 @@ def test_argument_errors():
     with pytest.raises(RuntimeError):
         cb.info_nce_loss(x.cpu(), 4, 2)
     with pytest.raises(ValueError):
-        cb.info_nce_loss(x, 4, 2, temperature=0.01)  # 1/tau > 43: outside the fixed-shift softmax range
+        cb.info_nce_loss(x, 4, 2, temperature=-0.5)  # 1/tau must be positive
+    assert torch.isfinite(cb.info_nce_loss(x, 4, 2, temperature=0.01))  # 1/tau = 100: no upper limit

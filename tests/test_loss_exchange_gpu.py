@@ -1,0 +1,203 @@
+"""The row-sharded EXCHANGE step on ONE GPU: W simulated ranks run the C-ABI phases in lockstep.
+
+A sharded job needs W GPUs, the round-end test box has one.  Every phase of the exchange step is an extern "C" call on
+caller-owned buffers, so W "ranks" can live on one device: each gets its own gathered buffers, statistics, scratch and
+slot arrays, the phases run rank by rank, and the place of a barrier across ranks is simply the end of a loop.  This
+covers the push kernels (csrc/shard_exchange.cu), the exchange-mode forward, the row sweep with its local strip, the
+gradient GEMM's per-owner epilogue stores (both the reduce-scatter form and the peer-slot form, whose "peer" pointers
+here point into the same device) and the split backward -- against the float64 oracle and the single-rank result.
+The real multi-GPU run of the same code (NCCL / NVLink) is tools/multigpu_check.py (tests/test_multigpu.py).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+PAIR_B = (1, 2, 2)
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6, 1 / 6), grad_outs=None):
+    """feats: list of 3 [N, d] CUDA tensors (or None); returns loss per rank, grads [3][N, d] float32, dscale."""
+    from clibd_b200 import _lib
+    from clibd_b200.loss import _DT, _column_slots
+    lib = _lib.load()
+    dev = labels.device
+    ref = next(f for f in feats if f is not None)
+    N, d = ref.shape
+    dtype = ref.dtype
+    n = N // world
+    assert n * world == N
+    dt = _DT[dtype]
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    w = _lib.float_array3(weights)
+    grad_outs = grad_outs or [1.0] * world
+    mode = _lib.MODE_EXCHANGE
+    nbytes = lib.clibd_loss_scratch_bytes(N, n, d, path, mode)
+    R = range(world)
+    # per-rank "symmetric" buffers
+    gx = [[None if f is None else torch.full_like(f, float("nan")) for f in feats] for _ in R]
+    ginv = [[None if f is None else torch.full((N,), float("nan"), device=dev) for f in feats] for _ in R]
+    glab = [torch.full((N,), -1, dtype=torch.int64, device=dev) for _ in R]
+    stats = [torch.full((9 * N,), float("nan"), device=dev) for _ in R]
+    colslots = [torch.full((world * 3 * N,), float("nan"), device=dev) for _ in R]
+    posslots = [torch.zeros(world * 4, dtype=torch.float64, device=dev) for _ in R]
+    pos_local = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in R]
+    pos = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in R]
+    scratch = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in R]
+    loss = [torch.empty((), device=dev) for _ in R]
+    gslots = [torch.zeros(world, device=dev) for _ in R]
+
+    def P(t):
+        return None if t is None else t.data_ptr()
+
+    # ---- all-gather by pushes
+    for r in R:
+        loc = [None if f is None else f[r * n:(r + 1) * n].contiguous() for f in feats]
+        lab = labels[r * n:(r + 1) * n].contiguous()
+        _lib.check(lib.clibd_shard_push_rows(
+            _lib.ptr_array3([P(t) for t in loc]), dt, lab.data_ptr(), n, d, r, world,
+            _lib.ptr_array([P(gx[q][m]) for q in R for m in range(3)]),
+            _lib.ptr_array([P(ginv[q][m]) for q in R for m in range(3)]),
+            _lib.ptr_array([glab[q].data_ptr() for q in R]), stream))
+    torch.cuda.synchronize()
+    for q in R:  # every rank now holds the whole batch, bit-identical
+        assert torch.equal(glab[q], labels)
+        for m in range(3):
+            if feats[m] is not None:
+                assert torch.equal(gx[q][m], feats[m])
+                assert torch.equal(ginv[q][m], ginv[0][m]) and bool(torch.isfinite(ginv[q][m]).all())
+    # ---- forward statistics of every rank, exchange, finish
+    scale_dev = torch.tensor([scale], device=dev)
+    for r in R:
+        st = stats[r].data_ptr()
+        _lib.check(lib.clibd_loss_forward_stats(
+            _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]), glab[r].data_ptr(), N, d,
+            r * n, n, 0.0, scale_dev.data_ptr(), w, path, mode, scratch[r].data_ptr(), nbytes, st, st + 12 * N,
+            st + 24 * N, pos_local[r].data_ptr(), stream))
+    for r in R:
+        _lib.check(lib.clibd_shard_push_stats(
+            stats[r].data_ptr(), pos_local[r].data_ptr(), N, r * n, n, r, world,
+            _lib.ptr_array([stats[q].data_ptr() for q in R]), _lib.ptr_array([colslots[q].data_ptr() for q in R]),
+            _lib.ptr_array([posslots[q].data_ptr() for q in R]), stream))
+    for r in R:
+        st = stats[r].data_ptr()
+        _lib.check(lib.clibd_shard_reduce_stats(colslots[r].data_ptr(), posslots[r].data_ptr(), N, world, st,
+                                                pos[r].data_ptr(), stream))
+        _lib.check(lib.clibd_loss_forward_finish(N, n, d, 0.0, w, path, mode, scratch[r].data_ptr(), nbytes, st,
+                                                 st + 12 * N, pos[r].data_ptr(), loss[r].data_ptr(), stream))
+    torch.cuda.synchronize()
+    used = [p for p in range(3) if weights[p] != 0.0]
+    for q in R[1:]:  # the exchanged statistics agree bit for bit on every rank
+        for p in used:
+            for blk in (0, 3, 6):
+                a0 = stats[0][(blk + p) * N:(blk + p + 1) * N]
+                assert torch.equal(stats[q][(blk + p) * N:(blk + p + 1) * N], a0)
+    # ---- backward: sweeps of every rank, then (barrier) the finish of every rank
+    first, count = _column_slots(weights, world)
+    go = [torch.tensor([g], device=dev) for g in grad_outs]
+    for r in R:
+        _lib.check(lib.clibd_shard_push_floats(go[r].data_ptr(), 1, r, world,
+                                               _lib.ptr_array([gslots[q].data_ptr() for q in R]), stream))
+    if form == "peer":
+        red = [torch.full((3, world, n, d), float("nan"), device=dev) for _ in R]
+        peer_red = _lib.ptr_array([red[q][p].data_ptr() for q in R for p in range(3)])
+    else:
+        part = [[None if f is None else torch.full((N, d), float("nan"), device=dev) for f in first] for _ in R]
+    for r in R:
+        st = stats[r].data_ptr()
+        _lib.check(lib.clibd_loss_backward_sweeps(
+            _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]), N, d, r * n, n, 0.0, w,
+            path, scratch[r].data_ptr(), nbytes, st + 24 * N,
+            None if form == "peer" else _lib.ptr_array3([P(t) for t in part[r]]),
+            peer_red if form == "peer" else None, r, world, stream))
+    torch.cuda.synchronize()
+    grads = [None if f is None else torch.zeros((N, d), device=dev) for f in feats]
+    dscale = torch.zeros(world, dtype=torch.float64, device=dev)
+    for r in R:
+        if form == "peer":
+            reduced = [None if f is None else red[r][f] for f in first]
+            slots = count
+        else:  # what NCCL's reduce-scatter(SUM) would deliver to rank r
+            reduced = [None if f is None else sum(part[q][m][r * n:(r + 1) * n] for q in R).contiguous()
+                       for m, f in enumerate(first)]
+            slots = [0 if f is None else 1 for f in first]
+        dx = [None if f is None else torch.empty((n, d), dtype=dtype, device=dev) for f in feats]
+        _lib.check(lib.clibd_loss_backward_finish(
+            _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]), N, d, r * n, n, 0.0, w,
+            path, scratch[r].data_ptr(), nbytes, _lib.ptr_array3([P(t) for t in reduced]), _lib.int_array(slots), 1.0,
+            gslots[r].data_ptr(), world, _lib.ptr_array3([P(t) for t in dx]), dscale[r:r + 1].data_ptr(), stream))
+        for m in range(3):
+            if dx[m] is not None:
+                grads[m][r * n:(r + 1) * n] = dx[m].float()
+    torch.cuda.synchronize()
+    return ([float(x) for x in loss], [None if g is None else g.cpu().numpy() for g in grads],
+            float(dscale.sum()))
+
+
+@pytest.mark.parametrize("form", ["reduce_scatter", "peer"])
+@pytest.mark.parametrize("N,d,nmod,world,operands,labels_kind", [
+    (1024, 768, 3, 4, "bf16", "multi"),   # BASELINE config-2 shape, 4 ranks of 256 rows
+    (1536, 768, 3, 2, "fp16", "multi"),   # two ranks of 768 rows (6 row tiles each)
+    (768, 200, 2, 3, "bf16", "onehot"),   # three ranks, d not a multiple of 64, image+dna only
+    (520, 768, 3, 2, "bf16", "zipf"),     # n = 260 per rank: ragged row tiles, long-tailed classes
+])
+def test_simulated_ranks_match_oracle(form, N, d, nmod, world, operands, labels_kind):
+    from clibd_b200 import _lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(21)
+    feats = [torch.randn(N, d, generator=gen).bfloat16() for _ in range(nmod)] + [None] * (3 - nmod)
+    if labels_kind == "onehot":
+        labels = torch.arange(N)
+    elif labels_kind == "zipf":
+        wz = 1.0 / torch.arange(1, max(2, N // 8) + 1, dtype=torch.float64)
+        labels = torch.multinomial(wz / wz.sum(), N, replacement=True, generator=gen)
+    else:
+        labels = torch.randint(0, max(1, N // 8), (N,), generator=gen)
+    scale = 1 / 0.07
+    ref = lo.contrastive_loss([None if f is None else f.float().numpy() for f in feats], labels.numpy(), scale)
+    weights = (1 / 6, 1 / 6, 1 / 6) if nmod == 3 else (0.5, 0.0, 0.0)
+    path = _lib.PATH_TC_BF16 if operands == "bf16" else _lib.PATH_TC_F16
+    grad_outs = [1.0 + 0.5 * r for r in range(world)]  # a different upstream gradient on every rank: the SUM scales dx
+    gsum = sum(grad_outs)
+    losses, grads, ds = _sharded_step([None if f is None else f.to(dev) for f in feats], labels.to(dev), scale, world,
+                                      path, form, weights, grad_outs)
+    for l in losses:
+        assert abs(l - ref["loss"]) <= 1e-3 * abs(ref["loss"])
+        assert l == losses[0]  # bit-identical on every rank
+    for i in range(3):
+        if ref["grads"][i] is not None:
+            assert _rel(grads[i], gsum * ref["grads"][i]) < 1e-3 + 2 ** -8, i
+    assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
+
+
+def test_simulated_ranks_trained_regime():
+    """Aligned modalities (G~ -> 2 T): the lam2 correction must survive the exchange -- lam2 of ALL rows comes from
+    the exchanged posrow, the row side subtracts it in the sweep's epilogue and the column side through the weighted
+    class sums."""
+    from clibd_b200 import _lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(21)
+    N, d, world, align = 1024, 768, 4, 0.7
+    labels = torch.randint(0, N // 4, (N,), generator=gen)
+    base = torch.randn(N, d, generator=gen)[labels]
+    # fp32 tensors holding fp16-representable values: gradients come back in fp32 (tests/test_loss_gpu.py,
+    # test_trained_regime_aligned_modalities: same inputs, same floor of 6e-3 set by the 16-bit S operands)
+    feats = [(align * base + (1 - align) * torch.randn(N, d, generator=gen)).half().float() for _ in range(3)]
+    scale = 1 / 0.07
+    ref = lo.contrastive_loss([f.numpy() for f in feats], labels.numpy(), scale)
+    for form in ("reduce_scatter", "peer"):
+        losses, grads, ds = _sharded_step([f.to(dev) for f in feats], labels.to(dev), scale, world, _lib.PATH_TC_F16, form)
+        assert abs(losses[0] - ref["loss"]) <= 1e-3 * max(abs(ref["loss"]), scale)
+        for i in range(3):
+            assert _rel(grads[i], world * ref["grads"][i]) < 6e-3, (form, i)

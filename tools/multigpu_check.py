@@ -28,39 +28,53 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (n, d, nmod, dtype, operands, tol) in [(192, 96, 3, torch.float32, None, 2e-5),
-                                               (512, 768, 3, torch.bfloat16, None, 6e-3),  # both sides round the gradient to bf16 (2^-9)
-                                               (333, 768, 2, torch.float16, None, 2e-3)]:
-        N = n * world
-        gen = torch.Generator().manual_seed(11)
-        full = [torch.randn(N, d, generator=gen).to(dtype).to(dev) for _ in range(nmod)] + [None] * (3 - nmod)
-        labels = torch.randint(0, max(1, N // 8), (N,), generator=gen).to(dev)
-        scale_full = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
-        leaves_full = [None if f is None else f.clone().requires_grad_(True) for f in full]
-        loss_full = cb.ContrastiveLoss(None, 1 / 0.07, tensor_core_operands=operands)(
-            leaves_full[0], leaves_full[1], leaves_full[2], labels, scale_full)
-        loss_full.backward()
-        sl = slice(rank * n, (rank + 1) * n)
-        leaves = [None if f is None else f[sl].clone().requires_grad_(True) for f in full]
-        scale = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
-        mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world,
-                          tensor_core_operands=operands)
-        loss = mod(leaves[0], leaves[1], leaves[2], labels[sl], scale)
-        (loss * 3.0).backward()
-        torch.cuda.synchronize()
-        e_loss = abs(float(loss) - float(loss_full)) / abs(float(loss_full))
-        errs = []
-        for lf, ll in zip(leaves_full, leaves):
-            if lf is None:
-                continue
-            ref = lf.grad[sl].float() * (3.0 * world)
-            errs.append(float((ll.grad.float() - ref).norm() / ref.norm()))
-        # d loss / d logit_scale is replicated: every rank holds the full-batch derivative times its grad_output
-        e_ds = abs(float(scale.grad) - 3.0 * float(scale_full.grad)) / abs(3.0 * float(scale_full.grad))
-        good = e_loss < 1e-5 and max(errs) < tol and e_ds < 1e-3
-        ok &= good
-        print(f"[rank {rank}] loss n={n} d={d} nmod={nmod} {dtype}: loss_err={e_loss:.2e} "
-              f"grad_err={max(errs):.2e} dscale_err={e_ds:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # every exchange form of the sharded step (clibd_b200/loss.py:_shard_mode): 'local' recomputes S for both gradients
+    # on every rank, 'nccl' computes S once and reduce-scatters the column-side partials with NCCL, 'peer' does the
+    # all-gather, the statistics exchange and that reduce-scatter as stores into peer-mapped memory over NVLink
+    cases = [(192, 96, 3, torch.float32, None, 2e-5),
+             (512, 768, 3, torch.bfloat16, None, 6e-3),  # both sides round the gradient to bf16 (2^-9)
+             (333, 768, 2, torch.float16, None, 2e-3),
+             (1024, 768, 3, torch.float32, "bf16", 1e-3),  # fp32 leaves: no output rounding
+             (2048, 768, 3, torch.float32, "fp16", 1e-3)]
+    for shard_mode in ("local", "nccl", "peer"):
+        os.environ["CLIBD_SHARD_MODE"] = shard_mode
+        for (n, d, nmod, dtype, operands, tol) in cases:
+            N = n * world
+            gen = torch.Generator().manual_seed(11)
+            full = [torch.randn(N, d, generator=gen).to(dtype).to(dev) for _ in range(nmod)] + [None] * (3 - nmod)
+            labels = torch.randint(0, max(1, N // 8), (N,), generator=gen).to(dev)
+            scale_full = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+            leaves_full = [None if f is None else f.clone().requires_grad_(True) for f in full]
+            loss_full = cb.ContrastiveLoss(None, 1 / 0.07, tensor_core_operands=operands)(
+                leaves_full[0], leaves_full[1], leaves_full[2], labels, scale_full)
+            loss_full.backward()
+            sl = slice(rank * n, (rank + 1) * n)
+            mod = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world,
+                              tensor_core_operands=operands)
+            # two steps through the same module: the second one reuses the exchange buffers of the first
+            for it in range(2):
+                leaves = [None if f is None else f[sl].clone().requires_grad_(True) for f in full]
+                scale = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+                loss = mod(leaves[0], leaves[1], leaves[2], labels[sl], scale)
+                g_out = 3.0 + rank  # a different upstream gradient per rank: the local rows receive the SUM
+                (loss * g_out).backward()
+            torch.cuda.synchronize()
+            g_sum = sum(3.0 + r for r in range(world))
+            e_loss = abs(float(loss.detach()) - float(loss_full.detach())) / abs(float(loss_full.detach()))
+            errs = []
+            for lf, ll in zip(leaves_full, leaves):
+                if lf is None:
+                    continue
+                ref = lf.grad[sl].float() * g_sum
+                errs.append(float((ll.grad.float() - ref).norm() / ref.norm()))
+            # d loss / d logit_scale is replicated: every rank holds the full-batch derivative times ITS grad_output
+            e_ds = abs(float(scale.grad) - g_out * float(scale_full.grad)) / abs(g_out * float(scale_full.grad))
+            good = e_loss < 1e-5 and max(errs) < tol and e_ds < 1e-3
+            ok &= good
+            print(f"[rank {rank}] {shard_mode:5s} loss n={n} d={d} nmod={nmod} {str(dtype)[6:]} operands={operands}: "
+                  f"loss_err={e_loss:.2e} grad_err={max(errs):.2e} dscale_err={e_ds:.2e} {'OK' if good else 'FAIL'}",
+                  flush=True)
+    os.environ.pop("CLIBD_SHARD_MODE", None)
 
     # ---- kNN: sharded keys + all-gather + merge == unsharded
     Q, K, d, k = 700, 20011, 768, 5

@@ -1,10 +1,13 @@
-"""Where does a row-sharded loss step spend its time?  Replays the phases of clibd_b200/loss.py:_FusedClipLossFn
-(collectives and C-ABI calls) at bench size with CUDA events around each phase; max over ranks, mean over steps.
+"""Where does a row-sharded loss step spend its time?  For each exchange form of clibd_b200/loss.py ('local' = two
+sweeps per pair, 'nccl' = S once + NCCL reduce-scatter, 'peer' = S once + stores into peer-mapped memory) the full
+fwd+bwd step and the forward alone are timed with CUDA events at bench size (max over ranks, mean over steps), and the
+library's own event timing of the tensor kernels gives the share that is NOT tensor work (the fixed cost).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port P \
-        tools/phase_timing.py
+        tools/phase_timing.py [N] [steps]
 """
 import ctypes
+import json
 import os
 import sys
 
@@ -12,8 +15,8 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import clibd_b200 as cb  # noqa: E402
 from clibd_b200 import _lib  # noqa: E402
-from clibd_b200.loss import _DT, _coalesced, pair_weights  # noqa: E402
 
 
 def main():
@@ -25,79 +28,73 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    N, d = int(os.environ.get("N", 32768)), 768
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    d = 768
     n = N // world
-    gen = torch.Generator().manual_seed(1 + rank)
+    gen = torch.Generator().manual_seed(1234 + rank)
     feats = [torch.randn(n, d, generator=gen).bfloat16().to(dev) for _ in range(3)]
     labels = torch.randint(0, N // 8, (n,), generator=gen).to(dev)
-    scale = torch.tensor([1 / 0.07], device=dev)
-    weights, _ = pair_weights([True, True, True], None, False)
-    path, dtype = _lib.PATH_TC_BF16, torch.bfloat16
-    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    names = ["gather", "inv_norm", "fwd_stats", "allreduce_stats", "finish", "allreduce_g", "backward", "allreduce_ds"]
-    acc = {k: 0.0 for k in names}
-    steps, warm = 12, 4
-    for it in range(steps + warm):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-        k = 0
-        ev[k].record(); k += 1
+    scale = torch.tensor(1 / 0.07, device=dev)
+    module = cb.ClipLoss(gather_with_grad=True, rank=rank, world_size=world) if world > 1 else cb.ContrastiveLoss(None, 1 / 0.07)
+
+    def sync():
         if world > 1:
-            all_labels = torch.empty(N, dtype=torch.int64, device=dev)
-            gathered = [torch.empty((N, d), dtype=dtype, device=dev) for _ in feats]
-            with _coalesced(None):
-                dist.all_gather_into_tensor(all_labels.view(dtype), labels.view(dtype))
-                for f, g in zip(feats, gathered):
-                    dist.all_gather_into_tensor(g, f)
-        else:
-            all_labels, gathered = labels, feats
-        ev[k].record(); k += 1
-        inv = []
-        for g in gathered:
-            iv = torch.empty(N, dtype=torch.float32, device=dev)
-            _lib.check(lib.clibd_row_inv_norm(g.data_ptr(), _DT[dtype], N, d, iv.data_ptr(), stream))
-            inv.append(iv)
-        ev[k].record(); k += 1
-        nbytes = lib.clibd_loss_scratch_bytes(N, n, d, path)
-        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        stats = torch.zeros(6 * N, dtype=torch.float32, device=dev)
-        pos = torch.zeros(3, dtype=torch.float64, device=dev)
-        xs = _lib.ptr_array3([g.data_ptr() for g in gathered])
-        ivs = _lib.ptr_array3([g.data_ptr() for g in inv])
-        w = _lib.float_array3(weights)
-        _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, all_labels.data_ptr(), N, d, rank * n, n, 0.0,
-                                                scale.data_ptr(), w, path, scratch.data_ptr(), nbytes, stats.data_ptr(),
-                                                stats.data_ptr() + 12 * N, pos.data_ptr(), stream))
-        ev[k].record(); k += 1
-        if world > 1:
-            dist.all_reduce(stats)
-            dist.all_reduce(pos)
-        ev[k].record(); k += 1
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(lib.clibd_loss_forward_finish(N, n, d, 0.0, w, path, scratch.data_ptr(), nbytes, stats.data_ptr(),
-                                                 stats.data_ptr() + 12 * N, pos.data_ptr(), loss.data_ptr(), stream))
-        ev[k].record(); k += 1
-        gsum = torch.ones(1, device=dev)
-        if world > 1:
-            dist.all_reduce(gsum)
-        ev[k].record(); k += 1
-        dxs = [torch.empty((n, d), dtype=dtype, device=dev) for _ in range(3)]
-        dscale = torch.zeros(1, dtype=torch.float64, device=dev)
-        outs = _lib.ptr_array3([g.data_ptr() for g in dxs])
-        _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, rank * n, n, 0.0, w, path, scratch.data_ptr(), nbytes,
-                                           1.0, gsum.data_ptr(), outs, dscale.data_ptr(), stream))
-        ev[k].record(); k += 1
-        if world > 1:
-            dist.all_reduce(dscale)
-        ev[k].record()
+            dist.barrier()
         torch.cuda.synchronize()
-        if it >= warm:
-            for i, nm in enumerate(names):
-                acc[nm] += ev[i].elapsed_time(ev[i + 1]) / steps
-    t = torch.tensor([acc[k] for k in names], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print("PHASES world", world, "N", N, {k: round(float(v), 3) for k, v in zip(names, t)}, "sum", round(float(t.sum()), 3))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.clibd_profile_enable(1)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        lib.clibd_profile_enable(0)
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        pm, pn = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+        lib.clibd_profile_read(pm, pn)
+        tensor_ms = torch.tensor([(pm[0] + pm[1] + pm[4]) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tensor_ms, op=dist.ReduceOp.MAX)
+        sync()
+        return float(ms), float(tensor_ms), [pm[0] / max(pn[0], 1), pm[1] / max(pn[1], 1), pm[4] / max(pn[4], 1)], \
+            [int(pn[0]) // steps, int(pn[1]) // steps, int(pn[4]) // steps]
+
+    def step():
+        leaves = [f.detach().requires_grad_(True) for f in feats]
+        loss = module(leaves[0], leaves[1], leaves[2], labels, scale)
+        loss.backward()
+        return loss
+
+    def fwd_only():
+        with torch.no_grad():
+            return module(feats[0], feats[1], feats[2], labels, scale)
+
+    modes = ["local", "nccl", "peer"] if world > 1 else ["single"]
+    for mode in modes:
+        if world > 1:
+            os.environ["CLIBD_SHARD_MODE"] = mode
+        try:
+            l0 = float(step())
+            ms, tms, per, cnt = timed(step)
+            fms, ftms, _, _ = timed(fwd_only)
+            if rank == 0:
+                print("PHASES " + json.dumps({
+                    "world": world, "N": N, "mode": mode, "loss": l0, "step_ms": round(ms, 4),
+                    "tensor_ms": round(tms, 4), "fixed_ms": round(ms - tms, 4), "fwd_ms": round(fms, 4),
+                    "fwd_tensor_ms": round(ftms, 4), "fwd_fixed_ms": round(fms - ftms, 4),
+                    "bwd_ms": round(ms - fms, 4), "bwd_fixed_ms": round((ms - fms) - (tms - ftms), 4),
+                    "kernel_ms": {"fwd_pair": round(per[0], 4), "bwd_pair": round(per[1], 4), "grad_gemm": round(per[2], 4)},
+                    "launches_per_step": {"fwd_pair": cnt[0], "bwd_pair": cnt[1], "grad_gemm": cnt[2]}}), flush=True)
+        except Exception as ex:  # noqa: BLE001
+            print(f"[rank {rank}] mode {mode} FAILED: {ex!r}", flush=True)
+            raise
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
