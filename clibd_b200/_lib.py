@@ -26,6 +26,7 @@ SIGNATURES = {
     "clibd_device_supported": (_INT, []),
     "clibd_kernel_launch_count": (_I64, []),
     "clibd_profile_enable": (_INT, [_INT]),
+    "clibd_graphs_active": (_INT, [_I64, _I64]),
     "clibd_profile_read": (_INT, [_P, _P]),
     "clibd_row_inv_norm": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),

@@ -9,6 +9,7 @@
 
 #include "../../include/clibd_b200.h"
 #include "common.cuh"
+#include "graph_cache.h"
 #include "loss_plan.h"
 
 namespace clibd {
@@ -33,10 +34,17 @@ __global__ void scale_set_kernel(float value, const float* __restrict__ dev, flo
 
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int64_t launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[PROF_SLOTS];
+
+bool profiling_enabled() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return g_prof_on;
+}
 
 ProfScope::ProfScope(int slot, cudaStream_t s) : slot_(slot), s_(s) {
     if (!g_prof_on) return;
@@ -86,7 +94,9 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         const int64_t num_jt = pair ? ceil_div(N, PAIR_BJ) : ceil_div(N, BWD_BJ);
         int64_t js = 1;
         double best = 0.0;
-        for (int64_t c = 1; c <= 8 && c <= num_jt; ++c) {
+        const char* js_env = std::getenv("CLIBD_JSPLIT_MAX");  // development: cap (or, negative, force) the column split
+        const int64_t js_cap = js_env ? std::atoll(js_env) : 8;
+        for (int64_t c = 1; c <= (js_cap > 0 ? js_cap : 1) && c <= num_jt; ++c) {
             const int64_t total = ctas * c;
             const double eff = static_cast<double>(total) / static_cast<double>(ceil_div(total, slots) * slots);
             if (eff > best + 0.02) {
@@ -94,7 +104,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
                 js = c;
             }
         }
-        p.jsplit = static_cast<int>(js);
+        p.jsplit = static_cast<int>(js_cap < 0 ? (-js_cap < num_jt ? -js_cap : num_jt) : js);
     } else {
         p.row_parts = ceil_div(N, SIMT_T);
         p.col_parts = ceil_div(n, SIMT_T);
@@ -121,12 +131,17 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     }
     p.off_u = take(sizeof(float) * 3 * N);
     p.off_v = take(sizeof(float) * 3 * N);
-    p.off_rowpart = take(sizeof(float) * p.row_parts * n);
-    p.off_colpart = take(sizeof(float) * p.col_parts * N);
+    // per-tile partial sums of the forward: one set per pair (so that ONE launch reduces all of them after the three
+    // forward kernels) while the three sets stay below 256 MB, a single shared set beyond that (N >= ~100k)
+    p.rowpart_elems = static_cast<size_t>(p.row_parts) * n;
+    p.colpart_elems = static_cast<size_t>(p.col_parts) * N;
+    p.part_sets = (3 * sizeof(float) * (p.rowpart_elems + p.colpart_elems) <= (size_t(256) << 20)) ? 3 : 1;
+    p.off_rowpart = take(sizeof(float) * p.rowpart_elems * p.part_sets);
+    p.off_colpart = take(sizeof(float) * p.colpart_elems * p.part_sets);
     p.off_posrow = take(sizeof(float) * n);
     p.off_cstart = take(sizeof(int32_t) * N);
     p.off_class_lo = take(sizeof(int32_t) * N);
-    p.off_ccS = take(sizeof(float) * N);
+    p.off_ccS = take(sizeof(float) * 3 * N);  // one per pair (S-once backward: all pairs prepared in one launch)
     p.off_posrow2 = take(sizeof(float) * 6 * n);
     // exchange mode: lam2 of ALL rows of every pair's row modality (the weighted class sums Qw need them)
     const bool want_exchange = mode == LOSS_MODE_EXCHANGE && n < N;
@@ -152,6 +167,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         p.strip_rows = rows < all ? rows : all;
         p.gt_ld = p.strip_rows;  // Gs[n local rows][strip columns]
         p.off_gt = take(2 * static_cast<size_t>(n) * p.gt_ld);
+        p.off_gt2 = take(2 * static_cast<size_t>(n) * p.gt_ld);  // (image, text) and (dna, text) feed one gradient GEMM
         p.npad_loc = round_up(n, 8);
         for (int m = 0; m < 3; ++m) {
             p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad_loc);
@@ -159,7 +175,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         }
     }
     p.off_dots = take(sizeof(float) * 3 * n);
-    p.off_red = take(sizeof(double) * 512);
+    p.off_red = take(sizeof(double) * 256 * 8);  // 256 block partials per reduction job
     const int64_t H = label_hash_slots(N);
     p.off_hown = take(sizeof(int32_t) * H);
     p.off_hmin = take(sizeof(int32_t) * H);
@@ -258,21 +274,65 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
     const int32_t* skey = at<int32_t>(scratch, plan.off_skey);
     const int32_t* sidx = at<int32_t>(scratch, plan.off_sidx);
     const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
-    float* ccS = at<float>(scratch, plan.off_ccS);
     void* gt = at<void>(scratch, plan.off_gt);
     int rc = 0;
     bool wrote_dxh[3] = {false, false, false};
     bool wrote_part[3] = {false, false, false};
+    // Per pair: the column coefficients in class-sorted order (ccS) and lam2 of every row the weighted class sums Qw
+    // touch -- all N rows (exchange mode: from the exchanged posrow) -- then Qw itself: rows of b see the lam2-weighted
+    // class sums of a (classes with a local member only).  One launch each for all pairs; the lam2-weighted sums of
+    // the image rows for (image, dna) and (image, text) share one pass over those rows.
+    {
+        SweepPrepJob sp[3];
+        ClassSumJob cj[3];
+        int nsp = 0, ncj = 0;
+        int job_of_mod[3] = {-1, -1, -1};
+        for (int p = 0; p < 3; ++p) {
+            if (pair_weight[p] == 0.f) continue;
+            const int a = kPairA[p];
+            float* lam2 = lam2_of_pair(scratch, plan, p);
+            sp[nsp].rowcoef = u + p * N;
+            sp[nsp].colcoef = v + p * N;
+            sp[nsp].posrow = plan.exchange ? ex.posrow + static_cast<int64_t>(p) * N
+                                           : at<float>(scratch, plan.off_posrow2) + static_cast<int64_t>(2 * p) * N;
+            sp[nsp].ccS = at<float>(scratch, plan.off_ccS) + static_cast<int64_t>(p) * N;
+            sp[nsp].lam2 = lam2;
+            ++nsp;
+            int j = job_of_mod[a];
+            if (j < 0 || cj[j].out[1] != nullptr) {
+                j = ncj++;
+                job_of_mod[a] = j;
+                cj[j].x = x[a];
+                cj[j].inv = inv_norm[a];
+                cj[j].lam2[0] = lam2;
+                cj[j].out[0] = at<float>(scratch, plan.off_Qw[p]);
+            } else {
+                cj[j].lam2[1] = lam2;
+                cj[j].out[1] = at<float>(scratch, plan.off_Qw[p]);
+            }
+        }
+        if ((rc = launch_sweep_prep_jobs(sp, nsp, sidx, cnt, N, 0, N, logit_scale, stream))) return rc;
+        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, skey, sidx, cnt, N, d, row0, n, stream))) return rc;
+    }
+    // Pairs are processed in groups that share their column modality b: (image, dna) -> dna; (image, text) and
+    // (dna, text) -> text.  Every pair of a group sweeps its rows into its own coefficient strip, then ONE gradient
+    // GEMM contracts the concatenated strips (equal pair weights; unequal ones fall back to one GEMM per pair).
+    int group_pairs[3][2];
+    int group_size[3] = {0, 0, 0};
+    int ngroups = 0;
     for (int p = 0; p < 3; ++p) {
         if (pair_weight[p] == 0.f) continue;
-        const int a = kPairA[p], b = kPairB[p];
-        float* lam2 = lam2_of_pair(scratch, plan, p);
-        // lam2 of every row the class sums Qw below will touch: all N rows (exchange mode: from the exchanged posrow)
-        const float* posrow = plan.exchange ? ex.posrow + static_cast<int64_t>(p) * N
-                                            : at<float>(scratch, plan.off_posrow2) + static_cast<int64_t>(2 * p) * N;
-        if ((rc = launch_sweep_prep(u + p * N, v + p * N, sidx, cnt, posrow, N, 0, N, logit_scale, ccS, lam2, stream)))
-            return rc;
-        float* dxh_a = at<float>(scratch, plan.off_dxh[a]);
+        int g = -1;
+        for (int k = 0; k < ngroups; ++k)
+            if (group_size[k] == 1 && kPairB[group_pairs[k][0]] == kPairB[p] && pair_weight[group_pairs[k][0]] == pair_weight[p])
+                g = k;
+        if (g < 0) g = ngroups++;
+        group_pairs[g][group_size[g]++] = p;
+    }
+    void* gts[2] = {gt, at<void>(scratch, plan.off_gt2)};
+    for (int g = 0; g < ngroups; ++g) {
+        const int p0 = group_pairs[g][0];
+        const int b = kPairB[p0];
         GradDest dest;
         for (int q = 0; q < MAX_PEERS; ++q) dest.base[q] = nullptr;
         int ksplit = 1, acc_grad = 0;
@@ -284,7 +344,8 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
             ksplit = plan.jsplit;
             acc_grad = wrote_dxh[b] ? 1 : 0;
         } else if (ex.peer_red != nullptr) {  // owners' slot arrays over NVLink, slot = this rank
-            for (int q = 0; q < ex.world; ++q) dest.base[q] = ex.peer_red[q * 3 + p];
+            CLIBD_REQUIRE(!wrote_part[b], "the peer form needs equal weights for the pairs that share a column modality");
+            for (int q = 0; q < ex.world; ++q) dest.base[q] = ex.peer_red[q * 3 + p0];
             dest.rows_per_dest = n;
             dest.slot_rows = n;
             dest.slot0 = ex.rank;
@@ -298,24 +359,28 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
         int strip = 0;
         for (int64_t c0 = 0; c0 < N; c0 += plan.strip_rows, ++strip) {
             const int64_t c1 = c0 + plan.strip_rows < N ? c0 + plan.strip_rows : N;
-            if ((rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]),
-                                            at<void>(scratch, plan.off_xhT[b]), N, plan.npad, d, plan.dpad, row0, n,
-                                            logit_scale, u + p * N, ccS, gscale, pair_weight[p], wrote_dxh[a] || strip > 0,
-                                            plan.jsplit, fmt_bf16, dxh_a, stream, /*self_mask=*/0, class_lo, cnt,
-                                            lam2 + row0, c0, c1, gt, plan.gt_ld)))
-                return rc;
-            if ((rc = tc_grad_from_strip(gt, plan.gt_ld, c1 - c0, c0, at<void>(scratch, plan.off_xhTo[a]), n, plan.npad_loc,
-                                         N, d, plan.dpad, sidx, gscale, pair_weight[p], acc_grad, ksplit, fmt_bf16, dest,
-                                         tc_num_sms(), stream)))
+            GradPart parts[2];
+            for (int k = 0; k < group_size[g]; ++k) {
+                const int p = group_pairs[g][k];
+                const int a = kPairA[p];
+                const float* lam2 = lam2_of_pair(scratch, plan, p);
+                const float* ccS = at<float>(scratch, plan.off_ccS) + static_cast<int64_t>(p) * N;
+                if ((rc = tc_backward_rows_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]),
+                                                at<void>(scratch, plan.off_xhT[b]), N, plan.npad, d, plan.dpad, row0, n,
+                                                logit_scale, u + p * N, ccS, gscale, pair_weight[p], wrote_dxh[a] || strip > 0,
+                                                plan.jsplit, fmt_bf16, at<float>(scratch, plan.off_dxh[a]), stream,
+                                                /*self_mask=*/0, class_lo, cnt, lam2 + row0, c0, c1, gts[k], plan.gt_ld)))
+                    return rc;
+                parts[k].gs = gts[k];
+                parts[k].xhT_x = at<void>(scratch, plan.off_xhTo[a]);
+            }
+            if ((rc = tc_grad_from_strip(parts, group_size[g], plan.gt_ld, c1 - c0, c0, n, plan.npad_loc, N, d, plan.dpad, sidx,
+                                         gscale, pair_weight[p0], acc_grad, ksplit, fmt_bf16, dest, tc_num_sms(), stream)))
                 return rc;
         }
-        wrote_dxh[a] = true;
+        for (int k = 0; k < group_size[g]; ++k) wrote_dxh[kPairA[group_pairs[g][k]]] = true;
         if (!plan.exchange) wrote_dxh[b] = true;
         else wrote_part[b] = true;
-        // rows of b see the lam2-weighted class sums of a (classes with a local member only)
-        if ((rc = launch_class_sums(x[a], dtype, inv_norm[a], skey, sidx, cnt, N, d, row0, n,
-                                    at<float>(scratch, plan.off_Qw[p]), stream, lam2)))
-            return rc;
     }
     return 0;
 }
@@ -378,6 +443,11 @@ const char* clibd_last_error(void) { return last_error().c_str(); }
 
 int64_t clibd_kernel_launch_count(void) { return g_launches.load(); }
 
+int clibd_graphs_active(int64_t n_global, int64_t n_local) {
+    const char* e = std::getenv("CLIBD_GRAPHS");
+    return (e == nullptr || std::atoi(e) != 0) && graph_worthwhile(n_global, n_local) ? 1 : 0;
+}
+
 int clibd_profile_enable(int enable) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = enable != 0;
@@ -421,7 +491,7 @@ int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, i
     return static_cast<int64_t>(make_loss_plan(n_global, n_local, d, path, true, mode).total);
 }
 
-int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
+static int loss_forward_stats_impl(const void* const x[3], int dtype, const float* const inv_norm[3],
                              const int64_t* labels, int64_t N, int64_t d, int64_t row0, int64_t n,
                              float logit_scale, const float* logit_scale_dev, const float pair_weight[3], int path,
                              int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
@@ -465,36 +535,71 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
     bool used[3] = {false, false, false};
     for (int p = 0; p < 3; ++p)
         if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
+    // Which 16-bit operand copies a modality needs.  Row operand (xh, input order): only the LOCAL rows are ever read
+    // (forward tiles and row sweeps of this rank's block).  Column operands (xhS class-sorted, xhT its transpose): all N
+    // rows, for modalities that appear as the column side -- every used modality when both directions are swept, only
+    // the pairs' second modality when S is computed once per pair (then image is never a column operand and text never
+    // a row operand: 400 MB of staging writes instead of 600 MB at N = 32768).  xhTo (transposed local rows in input
+    // order) is the K operand of the stored-coefficient GEMM.
+    bool row_op[3] = {false, false, false}, col_op[3] = {false, false, false};
+    for (int p = 0; p < 3; ++p) {
+        if (pair_weight[p] == 0.f) continue;
+        row_op[kPairA[p]] = col_op[kPairB[p]] = true;
+        if (!plan.shared_s) row_op[kPairB[p]] = col_op[kPairA[p]] = true;
+    }
+    // class sums Q[m] feed the positive term of the partner's rows: every pair's second modality, and the first one too
+    // when both directions are swept (S once per pair: the column side's target term uses the lam2-weighted Qw)
+    {
+        ClassSumJob cj[3];
+        int ncj = 0;
+        for (int m = 0; m < 3; ++m) {
+            if (!used[m] || !col_op[m]) continue;
+            cj[ncj].x = x[m];
+            cj[ncj].inv = inv_norm[m];
+            cj[ncj].out[0] = at<float>(scratch, plan.off_Q[m]);
+            ++ncj;
+        }
+        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, ls.skey, ls.sidx, cnt, N, d, row0, n, stream))) return rc;
+    }
     for (int m = 0; m < 3; ++m) {
         if (!used[m]) continue;
-        if ((rc = launch_class_sums(x[m], dtype, inv_norm[m], ls.skey, ls.sidx, cnt, N, d, row0, n, at<float>(scratch, plan.off_Q[m]), stream)))
+        if (!tc) continue;
+        if (col_op[m] &&
+            (rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16, nullptr,
+                                       at<void>(scratch, plan.off_xhT[m]), stream, ls.sidx,
+                                       at<void>(scratch, plan.off_xhS[m]))))
             return rc;
-        if (tc) {
-            // row operand in input order, column operands (xhS, xhT) in class-sorted order
-            if ((rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16,
-                                           at<void>(scratch, plan.off_xh[m]), at<void>(scratch, plan.off_xhT[m]), stream,
-                                           ls.sidx, at<void>(scratch, plan.off_xhS[m]))))
+        if (row_op[m]) {
+            const size_t esize = dtype == DT_F32 ? 4 : 2;
+            const void* xl = static_cast<const char*>(x[m]) + static_cast<size_t>(row0) * d * esize;
+            void* xh_loc = at<char>(scratch, plan.off_xh[m]) + static_cast<size_t>(row0) * plan.dpad * 2;
+            if ((rc = launch_make_operands(xl, dtype, inv_norm[m] + row0, n, d, plan.dpad, plan.npad_loc, fmt_bf16, xh_loc,
+                                           plan.shared_s ? at<void>(scratch, plan.off_xhTo[m]) : nullptr, stream)))
                 return rc;
-            if (plan.shared_s) {  // transposed operand of the LOCAL rows in input order (K operand of the
-                                  // stored-coefficient GEMM)
-                const size_t esize = dtype == DT_F32 ? 4 : 2;
-                const void* xl = static_cast<const char*>(x[m]) + static_cast<size_t>(row0) * d * esize;
-                if ((rc = launch_make_operands(xl, dtype, inv_norm[m] + row0, n, d, plan.dpad, plan.npad_loc, fmt_bf16,
-                                               nullptr, at<void>(scratch, plan.off_xhTo[m]), stream)))
-                    return rc;
-            }
         }
     }
-    float* rowpart = at<float>(scratch, plan.off_rowpart);
-    float* colpart = at<float>(scratch, plan.off_colpart);
     float* posrow2 = at<float>(scratch, plan.off_posrow2);
     double* red = at<double>(scratch, plan.off_red);
+    // The three forward kernels run back to back; their per-tile partial sums are reduced, the per-row positive dot
+    // products formed and summed afterwards, each in ONE launch for all pairs (one set of partial buffers per pair).
+    ReduceJob rj[6];
+    PosRowsJob pj[6];
+    SumJob sj[3];
+    int nrj = 0, npj = 0, nsj = 0;
+    auto flush_reduce = [&]() -> int {
+        const int r = launch_reduce_parts_jobs(rj, nrj, stream);
+        nrj = 0;
+        return r;
+    };
     for (int p = 0; p < 3; ++p) {
         if (pair_weight[p] == 0.f) {
             CLIBD_CHECK_CUDA(cudaMemsetAsync(pos + p, 0, sizeof(double), stream));
             continue;
         }
         const int a = kPairA[p], b = kPairB[p];
+        const int set = plan.part_sets == 3 ? p : 0;
+        float* rowpart = at<float>(scratch, plan.off_rowpart) + set * plan.rowpart_elems;
+        float* colpart = at<float>(scratch, plan.off_colpart) + set * plan.colpart_elems;
         if (tc) {
             rc = tc_forward_pair(at<void>(scratch, plan.off_xh[a]), at<void>(scratch, plan.off_xhS[b]), N, plan.dpad, row0,
                                  n, logit_scale, fmt_bf16, rowpart, colpart, stream);
@@ -503,27 +608,48 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
                                    colpart, stream);
         }
         if (rc) return rc;
-        if ((rc = launch_reduce_parts(rowpart, plan.row_parts, n, n, rowsum + p * N + row0, stream))) return rc;
+        rj[nrj].part = rowpart;
+        rj[nrj].parts = plan.row_parts;
+        rj[nrj].stride = n;
+        rj[nrj].len = n;
+        rj[nrj].out = rowsum + p * N + row0;
+        ++nrj;
         // the tcgen05 column sums come out in class-sorted column order: scatter them back to input order
-        if ((rc = launch_reduce_parts(colpart, plan.col_parts, N, N, colsum + p * N, stream, tc ? ls.sidx : nullptr)))
-            return rc;
+        rj[nrj].part = colpart;
+        rj[nrj].parts = plan.col_parts;
+        rj[nrj].stride = N;
+        rj[nrj].len = N;
+        rj[nrj].out = colsum + p * N;
+        rj[nrj].scatter = tc ? ls.sidx : nullptr;
+        ++nrj;
+        if (plan.part_sets == 1 && (rc = flush_reduce())) return rc;  // the next pair reuses the partial buffers
         // per-row positive dot products of both directions (direction 0 also gives the loss's positive term).
         // Exchange mode: direction 0 goes to the caller's [3, N] buffer at the local rows (the backward needs it for
-        // all rows), direction 1 is not used (no transposed sweep).
+        // all rows).  S once per pair: direction 1 is not used (no transposed sweep).
         float* posrow = plan.exchange ? posrow_out + static_cast<int64_t>(p) * N + row0 : posrow2 + (2 * p) * n;
-        if ((rc = launch_pos_rows(x[a], dtype, inv_norm[a], at<float>(scratch, plan.off_Q[b]), rep, d, row0, n, posrow,
-                                  stream)))
-            return rc;
-        if (!plan.shared_s &&
-            (rc = launch_pos_rows(x[b], dtype, inv_norm[b], at<float>(scratch, plan.off_Q[a]), rep, d, row0, n,
-                                  posrow + n, stream)))
-            return rc;
-        if ((rc = launch_sum_to_double(posrow, n, 1.0, red, pos + p, stream))) return rc;
+        pj[npj].xa = x[a];
+        pj[npj].inv_a = inv_norm[a];
+        pj[npj].Qb = at<float>(scratch, plan.off_Q[b]);
+        pj[npj].posrow = posrow;
+        ++npj;
+        if (!plan.shared_s) {
+            pj[npj].xa = x[b];
+            pj[npj].inv_a = inv_norm[b];
+            pj[npj].Qb = at<float>(scratch, plan.off_Q[a]);
+            pj[npj].posrow = posrow + n;
+            ++npj;
+        }
+        sj[nsj].in = posrow;
+        sj[nsj].len = n;
+        sj[nsj].out = pos + p;
+        ++nsj;
     }
-    return 0;
+    if ((rc = flush_reduce())) return rc;
+    if ((rc = launch_pos_rows_jobs(pj, npj, dtype, rep, d, row0, n, stream))) return rc;
+    return launch_sum_to_double_jobs(sj, nsj, 1.0, red, stream);
 }
 
-int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
+static int loss_forward_finish_impl(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
                               int path, int mode, void* scratch, int64_t scratch_bytes, const float* rowsum,
                               const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
     CLIBD_REQUIRE(N > 0 && d > 0 && path >= 0 && path <= 2 && mode >= 0 && mode <= 1, "bad shape");
@@ -536,7 +662,7 @@ int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale
                               at<double>(scratch, plan.off_red), loss_out, stream);
 }
 
-int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+static int loss_backward_impl(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
                         int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                         void* scratch, int64_t scratch_bytes, float grad_feat_scale, const float* grad_feat_scale_dev,
                         void* const dx[3],
@@ -650,7 +776,7 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
     return 0;
 }
 
-int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+static int loss_backward_sweeps_impl(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
                                int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                                void* scratch, int64_t scratch_bytes, const float* posrow, float* const part[3],
                                float* const peer_red[], int rank, int world, clibd_stream_t stream) {
@@ -680,7 +806,7 @@ int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* c
     return shared_s_sweeps(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch, plan, ex, stream);
 }
 
-int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+static int loss_backward_finish_impl(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
                                int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                                void* scratch, int64_t scratch_bytes, const float* const reduced[3],
                                const int reduced_slots[3], float grad_feat_scale, const float* grad_feat_scale_dev,
@@ -698,6 +824,89 @@ int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* c
     ScaleScope scale_scope(at<float>(scratch, plan.off_scale));
     return shared_s_finish(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, scratch, plan, reduced,
                            reduced_slots, grad_feat_scale, grad_feat_scale_dev, grad_count, dx, dscale_partial, stream);
+}
+
+// ---- the exported entry points: argument tuple -> CUDA-graph cache (graph_cache.h) -> the bodies above ---------------
+static GraphKey base_key(int tag, const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                         int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path, int mode,
+                         const void* scratch, int64_t scratch_bytes) {
+    GraphKey k;
+    k.add(tag).add_array(x, 3).add(dtype).add_array(inv_norm, 3).add(N).add(d).add(row0).add(n).add(logit_scale);
+    k.add_array(pair_weight, 3).add(path).add(mode).add(scratch).add(scratch_bytes);
+    // environment knobs that change the plan (development switches) are part of the key through the plan itself
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
+    k.add(plan.total).add(plan.jsplit).add(plan.shared_s).add(plan.strip_rows);
+    return k;
+}
+
+int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* const inv_norm[3],
+                             const int64_t* labels, int64_t N, int64_t d, int64_t row0, int64_t n,
+                             float logit_scale, const float* logit_scale_dev, const float pair_weight[3], int path,
+                             int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
+                             float* posrow_out, double* pos, clibd_stream_t stream) {
+    CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
+    GraphKey k = base_key(1, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, mode, scratch, scratch_bytes);
+    k.add(labels).add(logit_scale_dev).add(rowsum).add(colsum).add(posrow_out).add(pos);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_forward_stats_impl(x, dtype, inv_norm, labels, N, d, row0, n, logit_scale, logit_scale_dev, pair_weight,
+                                       path, mode, scratch, scratch_bytes, rowsum, colsum, posrow_out, pos, s);
+    });
+}
+
+int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
+                              int path, int mode, void* scratch, int64_t scratch_bytes, const float* rowsum,
+                              const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
+    CLIBD_REQUIRE(pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
+    GraphKey k;
+    k.add(2).add(N).add(n).add(d).add(logit_scale).add_array(pair_weight, 3).add(path).add(mode).add(scratch);
+    k.add(scratch_bytes).add(rowsum).add(colsum).add(pos).add(loss_out);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_forward_finish_impl(N, n, d, logit_scale, pair_weight, path, mode, scratch, scratch_bytes, rowsum, colsum,
+                                        pos, loss_out, s);
+    });
+}
+
+int clibd_loss_backward(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                        int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                        void* scratch, int64_t scratch_bytes, float grad_feat_scale, const float* grad_feat_scale_dev,
+                        void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
+    CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
+    GraphKey k = base_key(3, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 0, scratch, scratch_bytes);
+    k.add(grad_feat_scale).add(grad_feat_scale_dev).add_array(dx, dx ? 3 : 0).add(dscale_partial);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_backward_impl(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch, scratch_bytes,
+                                  grad_feat_scale, grad_feat_scale_dev, dx, dscale_partial, s);
+    });
+}
+
+int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                               int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                               void* scratch, int64_t scratch_bytes, const float* posrow, float* const part[3],
+                               float* const peer_red[], int rank, int world, clibd_stream_t stream) {
+    CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
+    CLIBD_REQUIRE(world >= 1 && world <= MAX_PEERS, "world must be in [1, 16]");
+    GraphKey k = base_key(4, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 1, scratch, scratch_bytes);
+    k.add(posrow).add_array(part, part ? 3 : 0).add_array(peer_red, peer_red ? world * 3 : 0).add(rank).add(world);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_backward_sweeps_impl(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch,
+                                         scratch_bytes, posrow, part, peer_red, rank, world, s);
+    });
+}
+
+int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
+                               int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
+                               void* scratch, int64_t scratch_bytes, const float* const reduced[3],
+                               const int reduced_slots[3], float grad_feat_scale, const float* grad_feat_scale_dev,
+                               int grad_count, void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
+    CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
+    GraphKey k = base_key(5, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 1, scratch, scratch_bytes);
+    k.add_array(reduced, reduced ? 3 : 0).add_array(reduced_slots, reduced_slots ? 3 : 0).add(grad_feat_scale);
+    k.add(grad_feat_scale_dev).add(grad_count).add_array(dx, dx ? 3 : 0).add(dscale_partial);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_backward_finish_impl(x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, scratch,
+                                         scratch_bytes, reduced, reduced_slots, grad_feat_scale, grad_feat_scale_dev,
+                                         grad_count, dx, dscale_partial, s);
+    });
 }
 
 }  // extern "C"

@@ -562,7 +562,8 @@ int tc_backward_rows_pair(const void* xh_x, const void* xh_y, const void* xhT_y,
     while (dpad % npieces != 0 || dpad / npieces > 256 || (dpad / npieces) % 16 != 0) ++npieces;
     const int piece_w = static_cast<int>(dpad / npieces);
     CUtensorMap tm_x, tm_y, tm_yt, tm_gs;
-    int rc = make_tmap_2d_16bit(&tm_x, xh_x, N, dpad, dpad, P_BK, 64, fmt_bf16);
+    // the row operand is staged for the local rows only: rows past row0 + n read as zeros (TMA fill)
+    int rc = make_tmap_2d_16bit(&tm_x, xh_x, row0 + n, dpad, dpad, P_BK, 64, fmt_bf16);
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_y, xh_y, N, dpad, dpad, P_BK, 128, fmt_bf16);
     if (rc) return rc;

@@ -252,7 +252,8 @@ int tc_forward_pair_cg2(const void* xh_a, const void* xh_b, int64_t N, int64_t d
     if (n == 0 || N == 0) return 0;
     CLIBD_REQUIRE(dpad % Q_BK == 0, "padded feature dim must be a multiple of 64");
     CUtensorMap tm_a, tm_b;
-    int rc = make_tmap_2d_16bit(&tm_a, xh_a, N, dpad, dpad, Q_BK, 128, fmt_bf16);
+    // the row operand is staged for the local rows only: rows past row0 + n read as zeros (TMA fill)
+    int rc = make_tmap_2d_16bit(&tm_a, xh_a, row0 + n, dpad, dpad, Q_BK, 128, fmt_bf16);
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_b, xh_b, N, dpad, dpad, Q_BK, 128, fmt_bf16);
     if (rc) return rc;

@@ -20,6 +20,11 @@
 // (the geometry of loss_fwd_pair.cu).  Rows of the strip are class-sorted column positions of the row sweep;
 // the epilogue scatters them to the input order through sidx.
 //
+// Two pairs that share their column modality -- (image, text) and (dna, text) -- are ONE launch: the K range is the
+// concatenation of both pairs' strips and row operands ([Gs_1; Gs_2]^T [Xhat_image; Xhat_dna]), so text's gradient is
+// accumulated in TMEM instead of a second read-modify-write pass over the output (or a second set of slots and a
+// second trip over NVLink in the sharded step).
+//
 // Row-sharded step (exchange mode, loss_api.cu): K = this rank's n local rows, the output is the rank's PARTIAL
 // gradient of all N rows of the column modality, and the epilogue sends every row straight to its owner: global
 // row g belongs to rank g / n, whose slot array is peer-mapped memory (GradDest) -- the reduce-scatter of the
@@ -48,8 +53,27 @@ constexpr int G_TN = 256;
 constexpr int G_SMEM_BARS = G_STAGES * G_STAGE_BYTES;
 constexpr int G_NUM_BARS = 2 * G_STAGES + 4;
 constexpr int G_SMEM_TMEMPTR = G_SMEM_BARS + G_NUM_BARS * 8;
-constexpr int G_SMEM_TOTAL = G_SMEM_TMEMPTR + 16;
+constexpr int G_SMEM_ROWPTR = G_SMEM_TMEMPTR + 16;  // float* [8 epilogue warps][32 rows]: destination row of every lane
+constexpr int G_SMEM_TOTAL = G_SMEM_ROWPTR + G_EPI_WARPS * 32 * 8;
 static_assert(G_SMEM_TOTAL <= 232448, "gradient GEMM kernel shared memory exceeds 227 KB");
+
+// In-register transpose of a 32 x 32 block held as v[k] = element (row = lane, column = k) of every lane: afterwards
+// v[k] = element (row = k, column = lane).  Five butterfly steps of 16 shuffles.
+__device__ __forceinline__ void transpose32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if ((k & s) == 0) {
+                const float send = up ? v[k] : v[k + s];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+                if (up) v[k] = recv;
+                else v[k + s] = recv;
+            }
+        }
+    }
+}
 
 struct GItem {
     int64_t mt, nt, ks;
@@ -65,8 +89,9 @@ __device__ __forceinline__ GItem g_item(int64_t t, int64_t num_nt, int ksplit) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
-loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_xt, int64_t Ms,
-                      int64_t strip0, int64_t Ntot, int64_t d, int64_t ld, int num_kb, int ksplit,
+loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_xt,
+                      const __grid_constant__ CUtensorMap tm_g1, const __grid_constant__ CUtensorMap tm_xt1, int num_kb0,
+                      int64_t Ms, int64_t strip0, int64_t Ntot, int64_t d, int64_t ld, int num_kb, int ksplit,
                       int kb_per_split, uint32_t idesc, const int32_t* __restrict__ sidx,
                       const float* __restrict__ gscale, float weight, int accumulate, const GradDest dest) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -78,6 +103,7 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
     uint64_t* tfull = bars + 2 * G_STAGES;
     uint64_t* tempty = bars + 2 * G_STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + G_SMEM_TMEMPTR);
+    float** rowptr = reinterpret_cast<float**>(smem + G_SMEM_ROWPTR);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -92,6 +118,10 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_g);
         prefetch_tmap(&tm_xt);
+        if (num_kb > num_kb0) {
+            prefetch_tmap(&tm_g1);
+            prefetch_tmap(&tm_xt1);
+        }
         for (int i = 0; i < G_STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -127,10 +157,15 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                 mbar_wait(&empty[slot], phase ^ 1);
                 if (elected) {
                     uint8_t* sa = smem + slot * G_STAGE_BYTES;
+                    // K blocks [0, num_kb0) come from the first (strip, row operand) part, the rest from the second
+                    const bool second = kb >= num_kb0;
+                    const CUtensorMap* tg = second ? &tm_g1 : &tm_g;
+                    const CUtensorMap* tx = second ? &tm_xt1 : &tm_xt;
+                    const int32_t kcrd = (second ? kb - num_kb0 : kb) * G_BK;
                     if (leader) mbar_arrive_expect_tx(&full[slot], 2u * G_STAGE_BYTES);
-                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa, arow, kb * G_BK, kEvictNormal);
-                    tma_load_2d_cg2(&tm_g, full_l0 + slot * 8, sa + G_A_BYTES / 2, arow + 64, kb * G_BK, kEvictNormal);
-                    tma_load_2d_cg2(&tm_xt, full_l0 + slot * 8, sa + G_A_BYTES, kb * G_BK, brow, kEvictLast);
+                    tma_load_2d_cg2(tg, full_l0 + slot * 8, sa, arow, kcrd, kEvictNormal);
+                    tma_load_2d_cg2(tg, full_l0 + slot * 8, sa + G_A_BYTES / 2, arow + 64, kcrd, kEvictNormal);
+                    tma_load_2d_cg2(tx, full_l0 + slot * 8, sa + G_A_BYTES, kcrd, brow, kEvictLast);
                 }
                 __syncwarp();
                 if (++slot == G_STAGES) {
@@ -193,6 +228,14 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
             const int64_t oq = orow / dest.rows_per_dest;       // owner of the row (0 unless peer form)
             const int64_t olr = orow - oq * dest.rows_per_dest;
             float* orp = dest.base[oq] + ((dest.slot0 + it.ks) * dest.slot_rows + olr) * ld;
+            // Stores go out ROW-CONTIGUOUS: a TMEM load leaves lane = row, register = column, i.e. a warp store would
+            // touch 32 rows with 16 bytes each -- 32 partial sectors, and over NVLink 32 minimum-size packets (measured
+            // with 7/8 of the rows remote: the GEMM took 2.6x its local time).  Each 32 x 32 block is transposed in
+            // registers first, so that one store instruction writes the 128 contiguous bytes of ONE row; the lanes'
+            // destination rows are published through shared memory.
+            __syncwarp();
+            rowptr[ew * 32 + lane] = row_ok ? orp : nullptr;
+            __syncwarp();
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
 #pragma unroll 1
@@ -207,7 +250,20 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                     if (lane == 0) mbar_arrive_cluster(tempty_l0 + as * 8);
                 }
                 const int64_t col0 = it.nt * G_TN + h * 128 + c * 32;
-                if (!row_ok || col0 >= d) continue;
+                if (col0 >= d) continue;
+                if (!accumulate && col0 + 32 <= d) {
+                    float f[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) f[k] = wgt * __uint_as_float(v[k]);
+                    transpose32(f, lane);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        float* rp = rowptr[ew * 32 + k];  // same address for the whole warp: one broadcast read
+                        if (rp != nullptr) rp[col0 + lane] = f[k];
+                    }
+                    continue;
+                }
+                if (!row_ok) continue;
                 if (vec_ok && col0 + 32 <= d) {
                     float4* o4 = reinterpret_cast<float4*>(orp + col0);
 #pragma unroll
@@ -248,21 +304,26 @@ loss_grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
 
 }  // namespace
 
-int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t K,
+int tc_grad_from_strip(const GradPart* parts, int nparts, int64_t gs_ld, int64_t Ms, int64_t strip0, int64_t K,
                        int64_t npad, int64_t Ntot, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale,
                        float weight, int accumulate, int ksplit, int fmt_bf16, const GradDest& dest, int num_sms,
                        cudaStream_t s) {
-    if (Ms == 0 || K == 0) return 0;
+    if (Ms == 0 || K == 0 || nparts == 0) return 0;
+    CLIBD_REQUIRE(nparts == 1 || nparts == 2, "the gradient GEMM concatenates at most two K parts");
     CLIBD_REQUIRE(ksplit >= 1 && gs_ld % 8 == 0 && gs_ld >= Ms, "bad strip geometry");
     CLIBD_REQUIRE(dest.rows_per_dest > 0 && ceil_div(Ntot, dest.rows_per_dest) <= MAX_PEERS, "bad gradient destination");
-    CUtensorMap tm_g, tm_xt;
-    // Gs [K rows, Ms strip columns (pitch gs_ld)]: rows beyond K / columns beyond Ms read as zero (TMA fill)
-    int rc = make_tmap_2d_16bit(&tm_g, gs, K, Ms, gs_ld, 64, G_BK, fmt_bf16);
-    if (rc) return rc;
-    rc = make_tmap_2d_16bit(&tm_xt, xhT_x, dpad, K, npad, G_BK, 128, fmt_bf16);
-    if (rc) return rc;
+    CUtensorMap tm_g[2], tm_xt[2];
+    for (int i = 0; i < 2; ++i) {
+        const GradPart& pt = parts[i < nparts ? i : 0];
+        // Gs [K rows, Ms strip columns (pitch gs_ld)]: rows beyond K / columns beyond Ms read as zero (TMA fill)
+        int rc = make_tmap_2d_16bit(&tm_g[i], pt.gs, K, Ms, gs_ld, 64, G_BK, fmt_bf16);
+        if (rc) return rc;
+        rc = make_tmap_2d_16bit(&tm_xt[i], pt.xhT_x, dpad, K, npad, G_BK, 128, fmt_bf16);
+        if (rc) return rc;
+    }
     CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_grad_gemm_kernel), G_SMEM_TOTAL));
-    const int num_kb = static_cast<int>(ceil_div(K, G_BK));
+    const int num_kb0 = static_cast<int>(ceil_div(K, G_BK));  // K blocks per part (a ragged tail block reads zeros)
+    const int num_kb = num_kb0 * nparts;
     const int slots = ksplit;  // the caller sums `slots` partial outputs: parts that get no K blocks are zeroed
     if (ksplit > num_kb) ksplit = num_kb;
     const int kb_per_split = static_cast<int>(ceil_div(num_kb, ksplit));
@@ -281,9 +342,9 @@ int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0
     const int pairs = static_cast<int>(items < max_pairs ? items : max_pairs);
     const uint32_t idesc = make_idesc_f16(256, G_TN, fmt_bf16 ? 1u : 0u, /*a_mn_major=*/1u);
     ProfScope prof(PROF_LOSS_GRAD_GEMM, s);
-    loss_grad_gemm_kernel<<<2 * pairs, G_THREADS, G_SMEM_TOTAL, s>>>(tm_g, tm_xt, Ms, strip0, Ntot, d, d, num_kb, ksplit,
-                                                                   kb_per_split, idesc, sidx, gscale, weight, accumulate,
-                                                                   dest);
+    loss_grad_gemm_kernel<<<2 * pairs, G_THREADS, G_SMEM_TOTAL, s>>>(tm_g[0], tm_xt[0], tm_g[1], tm_xt[1], num_kb0, Ms, strip0,
+                                                                   Ntot, d, d, num_kb, ksplit, kb_per_split, idesc, sidx,
+                                                                   gscale, weight, accumulate, dest);
     CLIBD_KERNEL_CHECK();
     return 0;
 }

@@ -28,6 +28,8 @@ struct LossPlan {
     int jsplit = 1;          // backward: column range split across CTAs (partials summed later)
     int64_t row_parts = 0;   // forward: number of row-sum partials per row
     int64_t col_parts = 0;   // forward: number of col-sum partials per column
+    size_t rowpart_elems = 0, colpart_elems = 0;  // floats of one set of forward partials
+    int part_sets = 1;       // 3: one set per pair (reduced together in one launch), 1: shared
     size_t off_rep = 0, off_cnt = 0, off_gscale = 0, off_scale = 0;  // off_scale: the call's logit scale on the device
     // xh: 16-bit unit rows in INPUT order (row operand); xhS / xhT: the same rows in CLASS-SORTED order and their
     // transpose (column operands: every row's positives are then one contiguous column range)
@@ -44,7 +46,7 @@ struct LossPlan {
     bool shared_s = false;
     bool exchange = false;
     int64_t strip_rows = 0, gt_ld = 0, npad_loc = 0;
-    size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0;
+    size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0, off_gt2 = 0;  // gt2: second strip (merged pairs)
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
     // label hash table (own/min/count per slot), rows sorted by class (keys, indices), sort input and CUB scratch
@@ -91,6 +93,47 @@ int launch_class_sums(const void* x, int dtype, const float* inv_norm, const int
 int launch_make_operands(const void* x, int dtype, const float* inv_norm, int64_t N, int64_t d, int64_t dpad,
                          int64_t npad, int fmt_bf16, void* xh, void* xhT, cudaStream_t s,
                          const int32_t* perm = nullptr, void* xhS = nullptr);
+// ---- batched forms: several independent jobs of the same kind in ONE launch (blockIdx.y = job).  A sharded step at
+// 8 GPUs is ~2.5 ms long; six 9-microsecond launches of a reduction are 2 % of it.
+constexpr int MAX_JOBS = 6;
+struct ClassSumJob {      // up to two weighted sums of the same rows in one pass: out[k][r] = sum_j w_k(j) xhat_j
+    const void* x = nullptr;
+    const float* inv = nullptr;
+    const float* lam2[2] = {nullptr, nullptr};  // weight 1 - lam2[j] / 2 (null: 1)
+    float* out[2] = {nullptr, nullptr};         // out[1] may be null
+};
+int launch_class_sums_jobs(const ClassSumJob* jobs, int njobs, int dtype, const int32_t* skey, const int32_t* sidx,
+                           const float* cnt, int64_t N, int64_t d, int64_t row0, int64_t n, cudaStream_t s);
+struct ReduceJob {
+    const float* part = nullptr;
+    int64_t parts = 0, stride = 0, len = 0;
+    float* out = nullptr;
+    const int32_t* scatter = nullptr;
+};
+int launch_reduce_parts_jobs(const ReduceJob* jobs, int njobs, cudaStream_t s);
+struct PosRowsJob {
+    const void* xa = nullptr;
+    const float* inv_a = nullptr;
+    const float* Qb = nullptr;
+    float* posrow = nullptr;
+};
+int launch_pos_rows_jobs(const PosRowsJob* jobs, int njobs, int dtype, const int32_t* rep, int64_t d, int64_t row0,
+                         int64_t n, cudaStream_t s);
+struct SumJob {
+    const float* in = nullptr;
+    int64_t len = 0;
+    double* out = nullptr;
+};
+// red: njobs * 256 doubles
+int launch_sum_to_double_jobs(const SumJob* jobs, int njobs, double mul, double* red, cudaStream_t s,
+                              const float* div_dev = nullptr);
+struct SweepPrepJob {
+    const float *rowcoef = nullptr, *colcoef = nullptr, *posrow = nullptr;
+    float *ccS = nullptr, *lam2 = nullptr;
+};
+int launch_sweep_prep_jobs(const SweepPrepJob* jobs, int njobs, const int32_t* sidx, const float* cnt, int64_t N,
+                           int64_t row0, int64_t n, float scale, cudaStream_t s);
+
 // class_lo[i] = first position of the class of row i in the class-sorted order (skey = sorted representatives)
 int launch_class_ranges(const int32_t* skey, const int32_t* rep, int64_t N, int32_t* cstart, int32_t* class_lo,
                         cudaStream_t s);
@@ -183,7 +226,13 @@ struct GradDest {
     int64_t slot_rows;
     int slot0;
 };
-int tc_grad_from_strip(const void* gs, int64_t gs_ld, int64_t Ms, int64_t strip0, const void* xhT_x, int64_t K,
+// parts: one or two (strip, transposed row operand) pairs whose K ranges are concatenated -- two modality pairs with the
+// same column modality and the same weight become one GEMM (both strips have K rows and pitch gs_ld)
+struct GradPart {
+    const void* gs = nullptr;
+    const void* xhT_x = nullptr;
+};
+int tc_grad_from_strip(const GradPart* parts, int nparts, int64_t gs_ld, int64_t Ms, int64_t strip0, int64_t K,
                        int64_t npad, int64_t Ntot, int64_t d, int64_t dpad, const int32_t* sidx, const float* gscale,
                        float weight, int accumulate, int ksplit, int fmt_bf16, const GradDest& dest, int num_sms,
                        cudaStream_t s);

@@ -552,7 +552,7 @@ int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad,
     if (!std::getenv("CLIBD_FWD_SINGLE"))
         return tc_forward_pair_cg2(xh_a, xh_b, N, dpad, row0, n, scale, fmt_bf16, rowpart, colpart, num_sms(), s);
     CUtensorMap tm_a, tm_b;
-    int rc = make_tmap_2d_16bit(&tm_a, xh_a, N, dpad, dpad, F_BK, FWD_BM, fmt_bf16);
+    int rc = make_tmap_2d_16bit(&tm_a, xh_a, row0 + n, dpad, dpad, F_BK, FWD_BM, fmt_bf16);  // local rows only
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_b, xh_b, N, dpad, dpad, F_BK, FWD_BN, fmt_bf16);
     if (rc) return rc;
@@ -575,7 +575,7 @@ int tc_backward_rows(const void* xh_x, const void* xh_y, const void* xhT_y, int6
     CLIBD_REQUIRE(dpad % B_BK == 0, "padded feature dim must be a multiple of 64");
     CLIBD_CHECK_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&loss_bwd_tc_kernel), B_SMEM_ALLOC));
     CUtensorMap tm_x, tm_y, tm_yt;
-    int rc = make_tmap_2d_16bit(&tm_x, xh_x, N, dpad, dpad, B_BK, BWD_BM, fmt_bf16);
+    int rc = make_tmap_2d_16bit(&tm_x, xh_x, row0 + n, dpad, dpad, B_BK, BWD_BM, fmt_bf16);  // local rows only
     if (rc) return rc;
     rc = make_tmap_2d_16bit(&tm_y, xh_y, N, dpad, dpad, B_BK, BWD_BJ, fmt_bf16);
     if (rc) return rc;

@@ -127,15 +127,16 @@ def _shard_mode(path, d, group, device):
 
 
 def _column_slots(weights, world):
-    """(first pair, slot count) of the received column-side partials per modality in the peer form: pair p's slot
-    array holds `world` slots; (image,dna) feeds dna, (image,text) and (dna,text) feed text (adjacent arrays)."""
+    """(pair whose slot array receives them, slot count) of the column-side gradient partials per modality in the peer
+    form.  (image,dna) feeds dna; (image,text) and (dna,text) feed text through ONE gradient GEMM (the library merges
+    pairs that share their column modality and weight), so text also receives `world` slots, in the slot array of its
+    first weighted pair."""
     first = [None, None, None]
     count = [0, 0, 0]
     for p, b in enumerate((1, 2, 2)):
-        if weights[p] != 0.0:
-            if first[b] is None:
-                first[b] = p
-            count[b] += world
+        if weights[p] != 0.0 and first[b] is None:
+            first[b] = p
+            count[b] = world
     return first, count
 
 

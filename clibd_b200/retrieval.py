@@ -180,15 +180,8 @@ def _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device, blocks=
     return s64, idx
 
 
-def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=None, process_group=None,
-               shard_keys: bool = False):
-    """normalise + search (+ shard merge).  Returns (similarities float32 [Q,k], indices int64 [Q,k])
-    as DEVICE tensors, sorted by descending similarity, lowest index first on ties."""
-    device = _device(device)
-    nk = keys_feature.shape[0]
-    if k > nk:
-        raise ValueError("max_k is larger than the number of keys")
-    q32 = normalize_rows(query_feature, device)
+def _shard_of(nk: int, shard_keys: bool, process_group):
+    """(world, rank, lo, hi): the contiguous key range [lo, hi) this rank searches."""
     world, rank = 1, 0
     if shard_keys:
         import torch.distributed as dist
@@ -196,7 +189,38 @@ def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=N
             raise RuntimeError("shard_keys=True needs an initialised torch.distributed process group")
         world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
     per = (nk + world - 1) // world
-    lo, hi = min(nk, rank * per), min(nk, (rank + 1) * per)
+    return world, rank, min(nk, rank * per), min(nk, (rank + 1) * per)
+
+
+def _merge_over_ranks(s64, idx, world, process_group):
+    """per-rank top-k lists (global indices) -> the global top-k on every rank: one all-gather + clibd_knn_merge."""
+    if world == 1:
+        return s64, s64.to(torch.float32), idx
+    import torch.distributed as dist
+    all_s = torch.empty((world,) + tuple(s64.shape), dtype=torch.float64, device=s64.device)
+    all_i = torch.empty((world,) + tuple(idx.shape), dtype=torch.int64, device=s64.device)
+    dist.all_gather_into_tensor(all_s, s64.contiguous(), group=process_group)
+    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=process_group)
+    return merge_topk(all_s, all_i)
+
+
+def _empty_lists(nq, k, device):
+    return (torch.full((nq, k), -torch.finfo(torch.float64).max, dtype=torch.float64, device=device),
+            torch.full((nq, k), -1, dtype=torch.int64, device=device))
+
+
+def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=None, process_group=None,
+               shard_keys: bool = False):
+    """normalise + search (+ shard merge).  Returns (similarities float32 [Q,k], indices int64 [Q,k])
+    as DEVICE tensors, sorted by descending similarity, lowest index first on ties.
+    shard_keys=True: every rank of `process_group` passes the same arguments, searches its contiguous share of the
+    keys and receives the merged global result (keys sharded over the GPUs, BASELINE.json north_star)."""
+    device = _device(device)
+    nk = keys_feature.shape[0]
+    if k > nk:
+        raise ValueError("max_k is larger than the number of keys")
+    q32 = normalize_rows(query_feature, device)
+    world, rank, lo, hi = _shard_of(nk, shard_keys, process_group)
     if hi > lo:
         host_keys = _as_host_tensor(keys_feature)
         if host_keys is not None and hi - lo >= _PIPELINE_MIN_KEYS:
@@ -204,17 +228,8 @@ def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=N
         else:
             s64, idx = _search_block(q32, normalize_rows(keys_feature[lo:hi], device), k, lo, mode)
     else:
-        s64 = torch.full((q32.shape[0], k), -torch.finfo(torch.float64).max, dtype=torch.float64, device=device)
-        idx = torch.full((q32.shape[0], k), -1, dtype=torch.int64, device=device)
-    if world > 1:
-        import torch.distributed as dist
-        all_s = torch.empty((world,) + tuple(s64.shape), dtype=torch.float64, device=device)
-        all_i = torch.empty((world,) + tuple(idx.shape), dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(all_s, s64.contiguous(), group=process_group)
-        dist.all_gather_into_tensor(all_i, idx.contiguous(), group=process_group)
-        _, s32, idx = merge_topk(all_s, all_i)
-    else:
-        s32 = s64.to(torch.float32)
+        s64, idx = _empty_lists(q32.shape[0], k, device)
+    _, s32, idx = _merge_over_ranks(s64, idx, world, process_group)
     return s32, idx
 
 
@@ -248,9 +263,10 @@ def make_prediction(query_feature, keys_feature, keys_label, with_similarity=Fal
 
 
 def find_closest_match(query_feature, keys_feature, keys_label, with_similarity=False, with_indices=False, max_k=5,
-                       mode="fp16", device=None):
+                       mode="fp16", device=None, process_group=None, shard_keys=False):
     """util.py:759-789: the same search, dictionary output."""
-    s32, idx = knn_search(query_feature, keys_feature, max_k, mode=mode, device=device)
+    s32, idx = knn_search(query_feature, keys_feature, max_k, mode=mode, device=device, process_group=process_group,
+                          shard_keys=shard_keys)
     indices = idx.cpu().numpy()
     out = {"pred_list": _labels_from_indices(indices, keys_label)}
     if with_similarity:
@@ -304,7 +320,9 @@ def accuracy_counts(idx: torch.Tensor, key_ids: torch.Tensor, query_ids: torch.T
     micro = torch.empty((nk, 4), dtype=torch.int64, device=device)
     chit = torch.empty((nk, 4, max_class), dtype=torch.int32, device=device)
     ccnt = torch.empty((nk, 4, max_class), dtype=torch.int32, device=device)
-    ks = (ctypes.c_int32 * nk)(*[int(k) for k in k_list])
+    # the reference slices pred[level][:k] (util.py:389, 573): a k beyond the number of retrieved neighbours looks at
+    # all of them (k_list need not be sorted: max_k is its LAST entry, util.py:607)
+    ks = (ctypes.c_int32 * nk)(*[min(int(k), int(kmax)) for k in k_list])
     with torch.cuda.device(device):
         _lib.check(lib.clibd_topk_accuracy(idx.contiguous().data_ptr(), Q, kmax, key_ids.contiguous().data_ptr(),
                                            key_ids.shape[0], query_ids.contiguous().data_ptr(), ks, nk, max_class,
@@ -395,11 +413,15 @@ def print_micro_and_macro_acc(acc_dict, k_list, args=None):
 
 
 def inference_and_print_result(keys_dict, seen_dict, unseen_dict, args=None, small_species_list=None, k_list=None,
-                               mode="fp16", device=None, verbose=True):
+                               mode="fp16", device=None, verbose=True, process_group=None, shard_keys=False):
     """util.py:601-700: every (query feature type, key feature type) pair of matching width is searched
     for the seen and unseen query sets; returns (acc_dict, per_class_acc, pred_dict) with the reference's
     schema.  Unlike the reference, the key set is normalised and staged once per key type (not once per
-    search) and labels are compared as integer ids on the GPU."""
+    search) and labels are compared as integer ids on the GPU.
+    shard_keys=True (every rank of `process_group` calls this with the same arguments): each rank normalises and
+    keeps only ITS contiguous share of every key type, searches it, and the per-rank candidate lists are merged by
+    one all-gather + clibd_knn_merge per search -- every rank returns the same dictionaries, bit-identical to the
+    unsharded call."""
     device = _device(device)
     acc_dict, per_class_acc = {}, {}
     if k_list is None:
@@ -455,8 +477,12 @@ def inference_and_print_result(keys_dict, seen_dict, unseen_dict, args=None, sma
                     or curr_keys_feature.shape[-1] != curr_seen_feature.shape[-1]
                     or curr_keys_feature.shape[-1] != curr_unseen_feature.shape[-1]):
                 continue
-            if key_feature_type not in key_norm_cache:
-                key_norm_cache[key_feature_type] = normalize_rows(curr_keys_feature, device)
+            nk = curr_keys_feature.shape[0]
+            if max_k > nk:
+                raise ValueError("max_k is larger than the number of keys")
+            world, _, lo, hi = _shard_of(nk, shard_keys, process_group)
+            if key_feature_type not in key_norm_cache:  # this rank's share, normalised and staged once per key type
+                key_norm_cache[key_feature_type] = normalize_rows(curr_keys_feature[lo:hi], device) if hi > lo else None
             k32 = key_norm_cache[key_feature_type]
             kid = key_ids_for(keys_label)
             entry = acc_dict[query_feature_type][key_feature_type]
@@ -465,7 +491,11 @@ def inference_and_print_result(keys_dict, seen_dict, unseen_dict, args=None, sma
             for split, feats, gts in (("seen", curr_seen_feature, seen_gt_label),
                                       ("unseen", curr_unseen_feature, unseen_gt_label)):
                 q32 = normalize_rows(feats, device)
-                _, idx, _ = search_normalized(q32, k32, max_k, mode=mode)
+                if k32 is not None:
+                    s64, idx = _search_block(q32, k32, max_k, lo, mode)
+                else:
+                    s64, idx = _empty_lists(q32.shape[0], max_k, device)
+                _, _, idx = _merge_over_ranks(s64, idx, world, process_group)
                 micro_acc, macro_acc, per_class = {}, {}, {}
                 for c0 in range(0, len(k_list), 4):
                     ks = list(k_list[c0:c0 + 4])

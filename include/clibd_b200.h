@@ -50,6 +50,10 @@ int64_t clibd_kernel_launch_count(void);
  * clibd_profile_read synchronises the recorded events, writes per-slot total milliseconds and launch
  * counts into host arrays of 8 entries each, and clears them. */
 int clibd_profile_enable(int enable);
+/* 1 when the loss entry points replay their launch sequence as a CUDA graph for this shape (launch-bound batches:
+ * n_global * n_local <= 2^28; CLIBD_GRAPHS=0 switches it off).  Event profiling bypasses the graphs, so a benchmark
+ * of such a shape takes its per-kernel timings in a separate pass. */
+int clibd_graphs_active(int64_t n_global, int64_t n_local);
 int clibd_profile_read(double* total_ms /* host [8] */, int64_t* launches /* host [8] */);
 
 /* ---- contrastive loss ------------------------------------------------------------

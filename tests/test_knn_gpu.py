@@ -181,6 +181,15 @@ def test_make_prediction_and_eval_entry_point_match_oracle():
                 assert acc[qt][kt][split]["macro_acc"] == rma_
                 assert per_class[qt][kt][split] == rpc_
     assert pred["seen_id"] == list(range(150))
+    # k_list need not be sorted: max_k is its LAST entry (util.py:607) and a larger k looks at all max_k neighbours
+    # (the reference slices pred[:k], util.py:389, 573)
+    acc2, _, _ = cb.inference_and_print_result(keys_dict, seen, unseen, args=None, k_list=[5, 1, 3], verbose=False)
+    rp3 = ko.make_prediction(seen["encoded_image_feature"], img_k, key_labels, max_k=3)
+    assert acc2["encoded_image_feature"]["encoded_image_feature"]["seen"]["micro_acc"] == \
+        ko.micro_accuracy_ref_style(rp3, seen_labels, [5, 1, 3])
+    with pytest.raises(ValueError, match="max_k"):
+        cb.inference_and_print_result({"label_list": key_labels[:2], "encoded_image_feature": img_k[:2]}, seen, unseen,
+                                      args=None, k_list=[1, 3], verbose=False)
 
 
 def test_large_search_properties():
@@ -204,3 +213,17 @@ def test_large_search_properties():
     srt = torch.sort(idx, dim=1).values
     assert torch.all(srt[:, 1:] != srt[:, :-1])
     assert int(nex) < Q // 10
+
+
+def test_benchmark_size_search_matches_oracle_on_sampled_queries():
+    """The benchmarked retrieval itself (100k queries x 1M keys, d = 768, k = 5, tools/synth.py data with 1000 exact
+    duplicate keys): 128 evenly spaced queries of the result are compared with the C oracle run over ALL 1M keys --
+    indices and float64 similarities bit-identical (about 10 s of host time on 16 cores)."""
+    from tools import knn_verify
+    if torch.cuda.get_device_properties(0).total_memory < 40 * 2 ** 30:
+        pytest.skip("needs ~10 GB of device memory")
+    out = knn_verify.run(100_000, 1_000_000, 128, torch.device("cuda:0"))
+    print(out)
+    assert out["indices_bit_exact"] and out["similarities_bit_exact"]
+    # what IndexFlatIP computes (float32 sgemm + top-k) ranks almost every query the same way on this data
+    assert out["fp32_indexflatip_restatement"]["top5_identical_as_sets"] > 0.99

@@ -97,6 +97,47 @@ def main():
     ok &= good
     print(f"[rank {rank}] knn shard merge bit-exact: {'OK' if good else 'FAIL'}", flush=True)
 
+    # ---- the public sharded entry points: knn_search / make_prediction / inference_and_print_result with
+    # shard_keys=True (every rank passes the same host arrays, searches its share, merges over NCCL) must return
+    # exactly what the unsharded call returns
+    import numpy as np
+    knp, qnp = keys.numpy(), q.numpy()
+    s_one, i_one = R.knn_search(qnp, knp, k, mode="fp16", device=dev)
+    s_sh, i_sh = R.knn_search(qnp, knp, k, mode="fp16", device=dev, shard_keys=True)
+    good = bool(torch.equal(i_sh, i_one) and torch.equal(s_sh, s_one) and torch.equal(i_one, i_all))
+    ok &= good
+    print(f"[rank {rank}] knn_search(shard_keys=True) == unsharded: {'OK' if good else 'FAIL'}", flush=True)
+    rng = np.random.default_rng(3)
+    Kk, Dd = 1501, 64   # not divisible by the world size; 64-d features
+    sp = rng.integers(0, 40, Kk)
+    cent = rng.standard_normal((40, Dd)).astype(np.float32)
+    kf = (cent[sp] + 0.3 * rng.standard_normal((Kk, Dd))).astype(np.float32)
+    kf[700:760] = kf[10:70]  # duplicates across the shard boundary
+    def lab(ids):
+        return [{"order": f"o{i % 3}", "family": f"f{i % 7}", "genus": f"g{i % 20}", "species": f"s{i}"} for i in ids]
+    qs, qu = rng.integers(0, 40, 90), rng.integers(0, 40, 70)
+    keys_dict = {"label_list": lab(sp), "encoded_image_feature": kf, "encoded_dna_feature": kf[::-1].copy(),
+                 "all_key_features": np.concatenate([kf, kf[::-1]], 0), "all_key_features_label": lab(sp) + lab(sp[::-1])}
+    seen = {"label_list": lab(qs), "file_name_list": list(range(90)),
+            "encoded_image_feature": (cent[qs] + 0.3 * rng.standard_normal((90, Dd))).astype(np.float32),
+            "encoded_dna_feature": (cent[qs] + 0.3 * rng.standard_normal((90, Dd))).astype(np.float32)}
+    unseen = {"label_list": lab(qu), "file_name_list": list(range(70)),
+              "encoded_image_feature": (cent[qu] + 0.5 * rng.standard_normal((70, Dd))).astype(np.float32),
+              "encoded_dna_feature": (cent[qu] + 0.5 * rng.standard_normal((70, Dd))).astype(np.float32)}
+    one = cb.inference_and_print_result(keys_dict, seen, unseen, args=None, k_list=[1, 3, 5], verbose=False, device=dev)
+    sh = cb.inference_and_print_result(keys_dict, seen, unseen, args=None, k_list=[1, 3, 5], verbose=False, device=dev,
+                                       shard_keys=True)
+    good = one == sh
+    ok &= good
+    print(f"[rank {rank}] inference_and_print_result(shard_keys=True) == unsharded (acc, per-class, predictions): "
+          f"{'OK' if good else 'FAIL'}", flush=True)
+    p_one = cb.make_prediction(seen["encoded_image_feature"], kf, keys_dict["label_list"], with_indices=True, max_k=5)
+    p_sh = cb.make_prediction(seen["encoded_image_feature"], kf, keys_dict["label_list"], with_indices=True, max_k=5,
+                              shard_keys=True)
+    good = p_one[0] == p_sh[0] and np.array_equal(p_one[1], p_sh[1])
+    ok &= good
+    print(f"[rank {rank}] make_prediction(shard_keys=True) == unsharded: {'OK' if good else 'FAIL'}", flush=True)
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
