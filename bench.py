@@ -574,13 +574,15 @@ def bench_knn(torch, dist, R, lib, dev, rank, world, timed, peak_tf):
     del queries, keys
 
     def step_e2e():
-        # host-resident queries and keys through the public entry point: every rank normalises the queries and copies
-        # ITS key shard block-wise on a copy stream while the previous block is normalised and screened; the shard
-        # merge is the all-gather + clibd_knn_merge inside knn_search
+        # host-resident queries and keys: every rank copies + normalises 1 / world of the queries (all-gathered over
+        # NVLink) and ITS key shard, block-wise on a copy stream while the previous block is normalised and screened;
+        # then the shard merge (all-gather + clibd_knn_merge)
         if world == 1:
             _, idx = R.knn_search(host_q, host_k, k, mode="fp16", device=dev)
             return idx.cpu()
-        qd = R.normalize_rows(host_q, dev)
+        # (knn_search(shard_keys=True) does exactly this for a key array every rank holds in full; here every rank
+        #  holds only its shard of the keys, as a sharded embedding store would)
+        qd = R.normalize_queries_sharded(host_q, dev, world, rank)
         s64, idx = R._search_host_keys_pipelined(qd, host_k, 0, host_k.shape[0], k, "fp16", dev, index_base=lo)
         all_s = torch.empty((world,) + tuple(s64.shape), dtype=torch.float64, device=dev)
         all_i = torch.empty((world,) + tuple(idx.shape), dtype=torch.int64, device=dev)

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -32,6 +33,14 @@ struct ProfScope {
 // (kernel, device) under a mutex, so that a process that drives several GPUs, or autograd's worker thread racing
 // the main thread on first use, never launches with the 48 KB default.  Returns a cudaError_t.
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
+
+// NVTX range around an entry point (header-only NVTX3: a no-op unless a profiler injects itself).  The reference has
+// no tracing at all; nsys / ncu timelines show the loss forward / backward and the retrieval as
+// named ranges.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define CLIBD_CHECK_CUDA(expr)                                                                    \
     do {                                                                                          \

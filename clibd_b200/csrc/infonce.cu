@@ -102,6 +102,7 @@ extern "C" {
 int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64_t M, int64_t d,
                           float inv_temperature, int path, void* scratch, int64_t scratch_bytes, float* rowsum,
                           float* loss_out, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_infonce_forward");
     CLIBD_REQUIRE(M > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
     const LossPlan plan = make_loss_plan(M, M, d, path, /*allow_shared_s=*/false);
     int rc = check_args(z, inv_norm, dtype, M, d, inv_temperature, path, scratch, scratch_bytes, plan);
@@ -152,6 +153,7 @@ int clibd_infonce_forward(const void* z, int dtype, const float* inv_norm, int64
 int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int64_t M, int64_t d,
                            float inv_temperature, int path, void* scratch, int64_t scratch_bytes,
                            float grad_scale, const float* grad_scale_dev, void* dz, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_infonce_backward");
     CLIBD_REQUIRE(M > 0 && d > 0 && path >= 0 && path <= 2, "bad shape");
     const LossPlan plan = make_loss_plan(M, M, d, path, /*allow_shared_s=*/false);
     int rc = check_args(z, inv_norm, dtype, M, d, inv_temperature, path, scratch, scratch_bytes, plan);
@@ -169,7 +171,7 @@ int clibd_infonce_backward(const void* z, int dtype, const float* inv_norm, int6
                                    w.cnt, w.lam2);
     } else {
         rc = simt_backward_rows(z, z, dtype, inv_norm, inv_norm, M, d, 0, M, scale, w.u, w.v, 1.0f, /*accumulate=*/0,
-                                w.dxh, stream, /*self_mask=*/1);
+                                w.dxh, stream, /*self_mask=*/1, plan.jsplit);
     }
     if (rc) return rc;
     NormBwdArgs a;

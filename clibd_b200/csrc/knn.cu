@@ -776,6 +776,7 @@ using namespace clibd;
 extern "C" {
 
 int clibd_knn_normalize(const void* x, int dtype, int64_t n, int64_t d, float* out, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_knn_normalize");
     CLIBD_REQUIRE(x && out && n >= 0 && d > 0, "null pointer or bad shape");
     CLIBD_REQUIRE(dtype == DT_F32 || dtype == kDT_F64, "knn_normalize takes float32 (0) or float64 (3)");
     if (n == 0) return 0;
@@ -796,6 +797,7 @@ int64_t clibd_knn_scratch_bytes(int64_t n_query, int64_t n_key, int64_t d, int k
 int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K, int64_t key_offset, int64_t d, int k,
                      int path, void* scratch, int64_t scratch_bytes, double* out_sims64, int64_t* out_idx,
                      int32_t* n_exhaustive, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_knn_search");
     CLIBD_REQUIRE(q32 && keys32 && out_sims64 && out_idx && n_exhaustive, "null pointer");
     CLIBD_REQUIRE(Q > 0 && K > 0 && d > 0, "bad shape");
     CLIBD_REQUIRE(k >= 1 && k <= SEL_KMAX, "k must be in [1,16]");
@@ -877,6 +879,7 @@ int clibd_knn_search(const float* q32, int64_t Q, const float* keys32, int64_t K
 
 int clibd_knn_merge(const double* sims64, const int64_t* idx, int parts, int64_t Q, int k, double* out_sims64,
                     float* out_sims32, int64_t* out_idx, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_knn_merge");
     CLIBD_REQUIRE(sims64 && idx && out_idx && parts >= 1 && Q > 0 && k >= 1, "bad arguments");
     CLIBD_REQUIRE(static_cast<int64_t>(parts) * k <= 32 * 32, "parts * k must be <= 1024");
     knn_merge_kernel<<<static_cast<unsigned>(ceil_div(Q * 32, 256)), 256, 0, stream>>>(sims64, idx, parts, Q, k, out_sims64,
@@ -888,6 +891,7 @@ int clibd_knn_merge(const double* sims64, const int64_t* idx, int parts, int64_t
 int clibd_topk_accuracy(const int64_t* idx, int64_t Q, int kmax, const int32_t* key_ids, int64_t K,
                         const int32_t* query_ids, const int32_t* k_list, int nk, int32_t max_class,
                         int64_t* micro_hits, int32_t* class_hit, int32_t* class_cnt, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_topk_accuracy");
     CLIBD_REQUIRE(idx && key_ids && query_ids && k_list && micro_hits && class_hit && class_cnt, "null pointer");
     CLIBD_REQUIRE(Q > 0 && K > 0 && kmax >= 1 && nk >= 1 && nk <= 4 && max_class >= 1, "bad arguments (nk <= 4)");
     int ks[4] = {0, 0, 0, 0};

@@ -108,7 +108,13 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     } else {
         p.row_parts = ceil_div(N, SIMT_T);
         p.col_parts = ceil_div(n, SIMT_T);
-        p.jsplit = 1;
+        // CUDA-core sweep: 32-row blocks; split the columns until about two waves of blocks exist (small batches)
+        const int64_t blocks = ceil_div(n, SIMT_BR) * ceil_div(d, 768);
+        int64_t js = ceil_div(2 * 148, blocks > 0 ? blocks : 1);
+        const int64_t steps = ceil_div(N, 32);
+        if (js > 8) js = 8;
+        if (js > steps) js = steps;
+        p.jsplit = static_cast<int>(js < 1 ? 1 : js);
     }
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -736,7 +742,8 @@ static int loss_backward_impl(const void* const x[3], int dtype, const float* co
                                       fmt_bf16, dxh, stream);
             } else {
                 rc = simt_backward_rows(x[m], x[other], dtype, inv_norm[m], inv_norm[other], N, d, row0, n, logit_scale,
-                                        rowcoef, colcoef, pair_weight[p], npart > 0, dxh, stream);
+                                        rowcoef, colcoef, pair_weight[p], npart > 0, dxh, stream, /*self_mask=*/0,
+                                        plan.jsplit);
             }
             if (rc) return rc;
             Qp[npart] = at<float>(scratch, plan.off_Q[other]);
@@ -844,6 +851,7 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
                              float logit_scale, const float* logit_scale_dev, const float pair_weight[3], int path,
                              int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
                              float* posrow_out, double* pos, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_forward_stats");
     CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
     GraphKey k = base_key(1, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, mode, scratch, scratch_bytes);
     k.add(labels).add(logit_scale_dev).add(rowsum).add(colsum).add(posrow_out).add(pos);
@@ -856,6 +864,7 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
 int clibd_loss_forward_finish(int64_t N, int64_t n, int64_t d, float logit_scale, const float pair_weight[3],
                               int path, int mode, void* scratch, int64_t scratch_bytes, const float* rowsum,
                               const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_forward_finish");
     CLIBD_REQUIRE(pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
     GraphKey k;
     k.add(2).add(N).add(n).add(d).add(logit_scale).add_array(pair_weight, 3).add(path).add(mode).add(scratch);
@@ -870,6 +879,7 @@ int clibd_loss_backward(const void* const x[3], int dtype, const float* const in
                         int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                         void* scratch, int64_t scratch_bytes, float grad_feat_scale, const float* grad_feat_scale_dev,
                         void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_backward");
     CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
     GraphKey k = base_key(3, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 0, scratch, scratch_bytes);
     k.add(grad_feat_scale).add(grad_feat_scale_dev).add_array(dx, dx ? 3 : 0).add(dscale_partial);
@@ -883,6 +893,7 @@ int clibd_loss_backward_sweeps(const void* const x[3], int dtype, const float* c
                                int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                                void* scratch, int64_t scratch_bytes, const float* posrow, float* const part[3],
                                float* const peer_red[], int rank, int world, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_backward_sweeps");
     CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
     CLIBD_REQUIRE(world >= 1 && world <= MAX_PEERS, "world must be in [1, 16]");
     GraphKey k = base_key(4, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 1, scratch, scratch_bytes);
@@ -898,6 +909,7 @@ int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* c
                                void* scratch, int64_t scratch_bytes, const float* const reduced[3],
                                const int reduced_slots[3], float grad_feat_scale, const float* grad_feat_scale_dev,
                                int grad_count, void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_backward_finish");
     CLIBD_REQUIRE(x && inv_norm && pair_weight && N > 0 && d > 0 && n >= 0, "null pointer or bad shape");
     GraphKey k = base_key(5, x, dtype, inv_norm, N, d, row0, n, logit_scale, pair_weight, path, 1, scratch, scratch_bytes);
     k.add_array(reduced, reduced ? 3 : 0).add_array(reduced_slots, reduced_slots ? 3 : 0).add(grad_feat_scale);

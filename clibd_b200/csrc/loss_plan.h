@@ -188,7 +188,7 @@ int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* in
 // dxh[n,d] (+)= weight * sum_j e_ij (rowcoef_i + colcoef_j) yhat_j   for local rows i of x
 int simt_backward_rows(const void* x, const void* y, int dtype, const float* inv_x, const float* inv_y, int64_t N,
                        int64_t d, int64_t row0, int64_t n, float scale, const float* rowcoef, const float* colcoef,
-                       float weight, int accumulate, float* dxh, cudaStream_t s, int self_mask = 0);
+                       float weight, int accumulate, float* dxh, cudaStream_t s, int self_mask = 0, int jsplit = 1);
 
 // ---- tcgen05 path (loss_tc.cu) --------------------------------------------------------
 int tc_forward_pair(const void* xh_a, const void* xh_b, int64_t N, int64_t dpad, int64_t row0, int64_t n, float scale,

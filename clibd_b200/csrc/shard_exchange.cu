@@ -137,6 +137,7 @@ extern "C" {
 int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t* labels_local, int64_t n, int64_t d,
                           int rank, int world, void* const peer_x[], float* const peer_inv[],
                           int64_t* const peer_labels[], clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_shard_push_rows");
     CLIBD_REQUIRE(x_local && labels_local && peer_x && peer_inv && peer_labels, "null pointer");
     CLIBD_REQUIRE(n > 0 && d > 0 && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "bad shape or rank");
     CLIBD_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, "dtype must be 0, 1 or 2");
@@ -181,6 +182,7 @@ int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t
 int clibd_shard_push_stats(const float* stats, const double* pos, int64_t N, int64_t row0, int64_t n, int rank,
                            int world, float* const peer_stats[], float* const peer_colslots[],
                            double* const peer_posslots[], clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_shard_push_stats");
     CLIBD_REQUIRE(stats && pos && peer_stats && peer_colslots && peer_posslots, "null pointer");
     CLIBD_REQUIRE(N > 0 && n > 0 && row0 >= 0 && row0 + n <= N && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world,
                   "bad shape or rank");

@@ -75,11 +75,22 @@ def pair_weights(present, bind_to=None, no_image_text_loss=False):
     return w, n_ordered
 
 
-def _select_path(dtype, operands):
-    if operands is None:
-        return {torch.float32: _lib.PATH_SIMT_F32, torch.bfloat16: _lib.PATH_TC_BF16,
-                torch.float16: _lib.PATH_TC_F16}[dtype]
-    return {"fp32": _lib.PATH_SIMT_F32, "bf16": _lib.PATH_TC_BF16, "fp16": _lib.PATH_TC_F16}[operands]
+_EXACT_PATH_MAX_BATCH = 1024
+
+
+def _select_path(dtype, operands, n_global, d):
+    """Which arithmetic the O(N^2 d) kernels use.  An explicit `tensor_core_operands` wins.  By default 16-bit inputs
+    take the tensor cores with their own operand type, and float32 inputs take
+      * the exact CUDA-core path up to a global batch of 1024 (BASELINE config 1: N = 256, parity 1e-5), and
+      * the tensor cores with FLOAT16 operands beyond (gradients within ~5e-5 of the float64 oracle, fp32 accumulation,
+        fp32 positive term and statistics): the CUDA-core sweep runs at ~10 TFLOP/s, so at the reference's own training
+        batch (500 per GPU x 8 = 4000 float32 embeddings out of its autocast block) the exact path would be slower than
+        the reference's cuBLAS calls.  tensor_core_operands="fp32" forces the exact path at any size."""
+    if operands is not None:
+        return {"fp32": _lib.PATH_SIMT_F32, "bf16": _lib.PATH_TC_BF16, "fp16": _lib.PATH_TC_F16}[operands]
+    if dtype == torch.float32:
+        return _lib.PATH_SIMT_F32 if n_global <= _EXACT_PATH_MAX_BATCH else _lib.PATH_TC_F16
+    return {torch.bfloat16: _lib.PATH_TC_BF16, torch.float16: _lib.PATH_TC_F16}[dtype]
 
 
 def _stream_ptr(device):
@@ -366,7 +377,7 @@ def _fused_loss(image_features, dna_features, text_features, labels, logit_scale
     scale_tensor = logit_scale if isinstance(logit_scale, torch.Tensor) else None
     # a tensor scale is handed over as a device pointer (no host read); scale_value is then unused
     scale_value = 0.0 if scale_tensor is not None else float(logit_scale)
-    path = _select_path(common, operands)
+    path = _select_path(common, operands, ref.shape[0] * max(1, world), ref.shape[1])
     return _FusedClipLossFn.apply(feats[0], feats[1], feats[2], labels, scale_tensor, scale_value, weights, path,
                                   group, world, rank, sum_grads)
 

@@ -113,6 +113,31 @@ def merge_topk(sims64_parts: torch.Tensor, idx_parts: torch.Tensor):
 
 _PIPELINE_MIN_KEYS = 1 << 17   # host-resident key sets at least this large are copied and searched block-wise
 _PIPELINE_BLOCKS = 4           # measured (tools/knn_blocks.py, 100k x 1M): 2 -> 157 ms, 4 -> 155, 8 -> 161, 16 -> 194
+_PIPELINE_BLOCK_KEYS = 1 << 18  # ... but no block below ~256k keys: every block pays its own re-rank pass
+
+
+def _pipeline_blocks(nkeys: int) -> int:
+    return max(1, min(_PIPELINE_BLOCKS, (nkeys + _PIPELINE_BLOCK_KEYS - 1) // _PIPELINE_BLOCK_KEYS))
+
+
+def normalize_queries_sharded(query_feature, device, world: int, rank: int, process_group=None) -> torch.Tensor:
+    """Normalised float32 queries on every rank of a sharded search.  HOST-resident queries are cut into `world`
+    row blocks: every rank copies and normalises only its block (1 / world of the host -> device traffic, which is
+    what bounds the end-to-end search once the keys are sharded) and the blocks are all-gathered over NVLink."""
+    host = _as_host_tensor(query_feature)
+    nq = query_feature.shape[0]
+    if world == 1 or host is None or nq < world * 1024:
+        return normalize_rows(query_feature, device)
+    import torch.distributed as dist
+    per = (nq + world - 1) // world
+    lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
+    d = host.shape[1]
+    mine = torch.zeros((per, d), dtype=torch.float32, device=device)
+    if hi > lo:
+        mine[:hi - lo] = normalize_rows(host[lo:hi], device)
+    out = torch.empty((world * per, d), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(out, mine, group=process_group)
+    return out[:nq]
 
 
 def _as_host_tensor(x):
@@ -140,12 +165,13 @@ def _search_block(q32, k32, k, key_offset, mode):
     return s64, idx
 
 
-def _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device, blocks=_PIPELINE_BLOCKS, index_base=0):
+def _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device, blocks=None, index_base=0):
     """Keys [lo, hi) live in host memory: copy them block by block on a copy stream into two staging buffers
     while the previous block is normalised and searched, then merge the per-block lists by (-sim, index) --
     the same order the shard merge uses, so the result equals the one-shot search bit for bit.  Hides the
     host->device copy of the key set (3 GB for 1M x 768 float32) behind the tensor-core screen.
     Returned indices are index_base + the row number inside host_keys."""
+    blocks = _pipeline_blocks(hi - lo) if blocks is None else blocks
     blocks = max(1, min(blocks, hi - lo))
     bounds = [lo + (hi - lo) * b // blocks for b in range(blocks + 1)]
     longest = max(bounds[b + 1] - bounds[b] for b in range(blocks))
@@ -219,8 +245,8 @@ def knn_search(query_feature, keys_feature, k: int, mode: str = "fp16", device=N
     nk = keys_feature.shape[0]
     if k > nk:
         raise ValueError("max_k is larger than the number of keys")
-    q32 = normalize_rows(query_feature, device)
     world, rank, lo, hi = _shard_of(nk, shard_keys, process_group)
+    q32 = normalize_queries_sharded(query_feature, device, world, rank, process_group)
     if hi > lo:
         host_keys = _as_host_tensor(keys_feature)
         if host_keys is not None and hi - lo >= _PIPELINE_MIN_KEYS:

@@ -87,7 +87,8 @@ def info_nce_loss(features: torch.Tensor, batch_size: int, n_views: int = 2, tem
         raise ValueError("temperature must be positive")
     if features.dtype not in _DT:
         features = features.to(torch.float32)
-    path = _select_path(features.dtype, tensor_core_operands)
+    m, d = features.shape
+    path = _select_path(features.dtype, tensor_core_operands, m if d <= 768 else 0, d)  # tcgen05 info-NCE: d <= 768
     return _InfoNCEFn.apply(features, 1.0 / float(temperature), path)
 
 

@@ -327,3 +327,26 @@ def test_benchmarked_configurations_match_the_float64_oracle(N):
         assert _rel(got, ref) < 1e-3, name
         # the whole gradient has the oracle's norm (a wrong block elsewhere would show here)
         assert abs(np.linalg.norm(grads[m].astype(np.float64)) - float(g[f"gradnorm_{name}"])) <= 1e-3 * float(g[f"gradnorm_{name}"])
+
+
+def test_default_path_for_float32_inputs():
+    """float32 embeddings (what the reference's bf16 autocast block hands to the loss: F.normalize returns float32):
+    up to a global batch of 1024 the exact CUDA-core path (parity 1e-5, BASELINE config 1), beyond it the tensor
+    cores with float16 operands -- loss within 1e-5, gradients within 2e-4 of the float64 oracle; `tensor_core_operands`
+    overrides either way (clibd_b200/loss.py:_select_path)."""
+    import clibd_b200 as cb
+    from clibd_b200 import _lib
+    from clibd_b200.loss import _select_path
+    assert _select_path(torch.float32, None, 1024, 768) == _lib.PATH_SIMT_F32
+    assert _select_path(torch.float32, None, 1025, 768) == _lib.PATH_TC_F16
+    assert _select_path(torch.float32, "fp32", 1 << 20, 768) == _lib.PATH_SIMT_F32
+    assert _select_path(torch.bfloat16, None, 16, 768) == _lib.PATH_TC_BF16
+    dev = torch.device("cuda:0")
+    feats, labels = _synthetic(1536, 768, 3, "multi", seed=17, dtype=torch.float32)
+    scale = torch.tensor(1 / 0.07)
+    ref = lo.contrastive_loss([f.numpy() for f in feats], labels.numpy(), float(scale))
+    loss, grads, ds = _run(cb.ContrastiveLoss(None, 1 / 0.07), [f.to(dev) for f in feats], labels.to(dev), scale.to(dev))
+    assert abs(loss - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    for i in range(3):
+        assert _rel(grads[i], ref["grads"][i]) < 2e-4, i
+    assert abs(ds - ref["dlogit_scale"]) <= 2e-4 * abs(ref["dlogit_scale"])
