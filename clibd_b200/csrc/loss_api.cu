@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <set>
+#include <unordered_map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -74,8 +75,39 @@ cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_shared_s, int mode) {
+PlanKnobs plan_knobs_from_env() {
+    PlanKnobs k;
+    if (const char* e = std::getenv("CLIBD_SHARED_S_MIN_N")) k.shared_min_n = std::atoll(e);  // tests force the path
+    if (const char* e = std::getenv("CLIBD_GT_STRIP_MB")) k.strip_mb = std::atof(e);
+    if (const char* e = std::getenv("CLIBD_JSPLIT_MAX")) k.js_cap = std::atoll(e);  // cap (negative: force) the split
+    k.two_sweeps = std::getenv("CLIBD_BWD_TWO_SWEEPS") != nullptr;
+    k.bwd_single = std::getenv("CLIBD_BWD_SINGLE") != nullptr;
+    return k;
+}
+
+static std::mutex g_knob_mu;
+static std::unordered_map<const void*, PlanKnobs> g_knobs;
+
+void remember_plan_knobs(const void* scratch, const PlanKnobs& k) {
+    std::lock_guard<std::mutex> lk(g_knob_mu);
+    if (g_knobs.size() > 1024) g_knobs.clear();
+    g_knobs[scratch] = k;
+}
+
+PlanKnobs plan_knobs_for(const void* scratch) {
+    {
+        std::lock_guard<std::mutex> lk(g_knob_mu);
+        auto it = g_knobs.find(scratch);
+        if (it != g_knobs.end()) return it->second;
+    }
+    return plan_knobs_from_env();
+}
+
+LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_shared_s, int mode,
+                        const PlanKnobs* knobs_in) {
+    const PlanKnobs knobs = knobs_in ? *knobs_in : plan_knobs_from_env();
     LossPlan p;
+    p.bwd_single = knobs.bwd_single;
     p.N = N;
     p.n = n;
     p.d = d;
@@ -94,8 +126,7 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         const int64_t num_jt = pair ? ceil_div(N, PAIR_BJ) : ceil_div(N, BWD_BJ);
         int64_t js = 1;
         double best = 0.0;
-        const char* js_env = std::getenv("CLIBD_JSPLIT_MAX");  // development: cap (or, negative, force) the column split
-        const int64_t js_cap = js_env ? std::atoll(js_env) : 8;
+        const int64_t js_cap = knobs.js_cap;
         for (int64_t c = 1; c <= (js_cap > 0 ? js_cap : 1) && c <= num_jt; ++c) {
             const int64_t total = ctas * c;
             const double eff = static_cast<double>(total) / static_cast<double>(ceil_div(total, slots) * slots);
@@ -155,18 +186,16 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
     // Single-GPU tcgen05 pair path: S is computed once per pair; the row sweep stores its 16-bit coefficients
     // transposed in a strip buffer (CLIBD_GT_STRIP_MB, default 2304 MB = the whole column range at
     // N = 32768, and never fewer than 18944 columns) and the other side's gradient is a plain GEMM over that strip.
-    // (below N = 6144 the step is launch-bound and the extra staging launches cost more than the sweep they save:
-    //  measured 0.88 vs 0.81 ms at N = 4096, 2.26 vs 2.56 ms at N = 8192, three modalities)
-    const char* min_env = std::getenv("CLIBD_SHARED_S_MIN_N");  // tests force the path at oracle-sized batches
-    const int64_t shared_min_n = min_env ? std::atoll(min_env) : 6144;
+    // (used from N = 4096 up: measured 0.53 vs 0.61 ms per step at N = 4096, three modalities, tools/small_batch_probe.py;
+    //  at N = 2048 the step is bound by the host's launch rate either way)
+    const int64_t shared_min_n = knobs.shared_min_n;
     // Row-sharded exchange mode: the same S-once backward on the local rows of every pair's row modality; the caller
     // asked for it explicitly, so only the shape limits of the pair kernels apply.
     p.exchange = allow_shared_s && tc && want_exchange && p.dpad <= PAIR_DCH;
     p.shared_s = p.exchange || (allow_shared_s && tc && n == N && N >= shared_min_n && p.dpad <= PAIR_DCH &&
-                                !std::getenv("CLIBD_BWD_TWO_SWEEPS") && !std::getenv("CLIBD_BWD_SINGLE"));
+                                !knobs.two_sweeps && !knobs.bwd_single);
     if (p.shared_s) {
-        const char* env = std::getenv("CLIBD_GT_STRIP_MB");
-        const double budget = (env ? std::atof(env) : 2304.0) * 1048576.0;
+        const double budget = knobs.strip_mb * 1048576.0;
         int64_t rows = static_cast<int64_t>(budget / (2.0 * static_cast<double>(n))) / 256 * 256;
         if (rows < 74 * 256) rows = 74 * 256;  // at least one 256-row tile per CTA pair and feature tile
         const int64_t all = round_up(N, 256);
@@ -402,9 +431,10 @@ static int shared_s_finish(const void* const x[3], int dtype, const float* const
     double* red = at<double>(scratch, plan.off_red);
     int rc = 0;
     int n_mod_used = 0;
+    NormBwdArgs all[3];
     for (int m = 0; m < 3; ++m) {
         if (np.nparts[m] == 0) continue;
-        NormBwdArgs a;
+        NormBwdArgs& a = all[n_mod_used];
         a.x = x[m];
         a.dtype = dtype;
         a.inv_norm = inv_norm[m];
@@ -430,9 +460,9 @@ static int shared_s_finish(const void* const x[3], int dtype, const float* const
         a.grad_scale_dev_count = grad_count;
         a.dx = dx ? dx[m] : nullptr;
         a.dots = dots + n_mod_used * n;
-        if ((rc = launch_normalize_bwd(a, stream))) return rc;
         ++n_mod_used;
     }
+    if ((rc = launch_normalize_bwd_multi(all, n_mod_used, stream))) return rc;
     return launch_sum_to_double(dots, static_cast<int64_t>(n_mod_used) * n, 0.5, red, dscale_partial, stream,
                                 scale_dev_ptr());
 }
@@ -503,7 +533,9 @@ static int loss_forward_stats_impl(const void* const x[3], int dtype, const floa
                              int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
                              float* posrow_out, double* pos, clibd_stream_t stream) {
     CLIBD_REQUIRE(mode == LOSS_MODE_LOCAL || mode == LOSS_MODE_EXCHANGE, "mode must be 0 or 1");
-    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
+    const PlanKnobs knobs = plan_knobs_from_env();
+    remember_plan_knobs(scratch, knobs);  // finish / backward of this step lay the scratch out the same way
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(labels && rowsum && colsum && pos, "null output pointer");
@@ -659,7 +691,8 @@ static int loss_forward_finish_impl(int64_t N, int64_t n, int64_t d, float logit
                               int path, int mode, void* scratch, int64_t scratch_bytes, const float* rowsum,
                               const float* colsum, const double* pos, float* loss_out, clibd_stream_t stream) {
     CLIBD_REQUIRE(N > 0 && d > 0 && path >= 0 && path <= 2 && mode >= 0 && mode <= 1, "bad shape");
-    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
+    const PlanKnobs knobs = plan_knobs_for(scratch);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
     CLIBD_REQUIRE(scratch && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
     CLIBD_REQUIRE(rowsum && colsum && pos && loss_out, "null pointer");
     ScaleScope scale_scope(at<float>(scratch, plan.off_scale));  // written by clibd_loss_forward_stats
@@ -673,7 +706,8 @@ static int loss_backward_impl(const void* const x[3], int dtype, const float* co
                         void* scratch, int64_t scratch_bytes, float grad_feat_scale, const float* grad_feat_scale_dev,
                         void* const dx[3],
                         double* dscale_partial, clibd_stream_t stream) {
-    const LossPlan plan = make_loss_plan(N, n, d, path);
+    const PlanKnobs knobs = plan_knobs_for(scratch);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_LOCAL, &knobs);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(dscale_partial != nullptr, "null dscale_partial");
@@ -696,7 +730,7 @@ static int loss_backward_impl(const void* const x[3], int dtype, const float* co
     const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
     float* ccS = at<float>(scratch, plan.off_ccS);
     float* dots = at<float>(scratch, plan.off_dots);
-    const bool use_pair = tc && pair_backward_supported(plan.dpad) && !std::getenv("CLIBD_BWD_SINGLE");
+    const bool use_pair = tc && pair_backward_supported(plan.dpad) && !plan.bwd_single;
     double* red = at<double>(scratch, plan.off_red);
     int n_mod_used = 0;
     for (int m = 0; m < 3; ++m) {
@@ -787,7 +821,8 @@ static int loss_backward_sweeps_impl(const void* const x[3], int dtype, const fl
                                int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path,
                                void* scratch, int64_t scratch_bytes, const float* posrow, float* const part[3],
                                float* const peer_red[], int rank, int world, clibd_stream_t stream) {
-    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE);
+    const PlanKnobs knobs = plan_knobs_for(scratch);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE, &knobs);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(plan.exchange, "clibd_loss_backward_sweeps needs a row-sharded tensor-core plan (n_local < n_global, d <= 768)");
@@ -818,7 +853,8 @@ static int loss_backward_finish_impl(const void* const x[3], int dtype, const fl
                                void* scratch, int64_t scratch_bytes, const float* const reduced[3],
                                const int reduced_slots[3], float grad_feat_scale, const float* grad_feat_scale_dev,
                                int grad_count, void* const dx[3], double* dscale_partial, clibd_stream_t stream) {
-    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE);
+    const PlanKnobs knobs = plan_knobs_for(scratch);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, LOSS_MODE_EXCHANGE, &knobs);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
     CLIBD_REQUIRE(plan.exchange, "clibd_loss_backward_finish needs a row-sharded tensor-core plan");
@@ -841,8 +877,9 @@ static GraphKey base_key(int tag, const void* const x[3], int dtype, const float
     k.add(tag).add_array(x, 3).add(dtype).add_array(inv_norm, 3).add(N).add(d).add(row0).add(n).add(logit_scale);
     k.add_array(pair_weight, 3).add(path).add(mode).add(scratch).add(scratch_bytes);
     // environment knobs that change the plan (development switches) are part of the key through the plan itself
-    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode);
-    k.add(plan.total).add(plan.jsplit).add(plan.shared_s).add(plan.strip_rows);
+    const PlanKnobs knobs = tag == 1 ? plan_knobs_from_env() : plan_knobs_for(scratch);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
+    k.add(plan.total).add(plan.jsplit).add(plan.shared_s).add(plan.strip_rows).add(plan.bwd_single);
     return k;
 }
 

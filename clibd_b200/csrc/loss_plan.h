@@ -25,6 +25,7 @@ constexpr int SIMT_BR = 32;   // backward rows per block
 struct LossPlan {
     int64_t N = 0, n = 0, d = 0, dpad = 0, npad = 0;
     int path = 0;
+    bool bwd_single = false;  // development switch: single-CTA sweep instead of the CTA-pair kernel
     int jsplit = 1;          // backward: column range split across CTAs (partials summed later)
     int64_t row_parts = 0;   // forward: number of row-sum partials per row
     int64_t col_parts = 0;   // forward: number of col-sum partials per column
@@ -59,7 +60,22 @@ struct LossPlan {
 // rows are sharded), 1 = exchange (S once per pair on every rank; column-side gradient partials are exchanged)
 constexpr int LOSS_MODE_LOCAL = 0;
 constexpr int LOSS_MODE_EXCHANGE = 1;
-LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path, bool allow_shared_s = true, int mode = 0);
+// Development / test switches read from the environment (CLIBD_SHARED_S_MIN_N, CLIBD_GT_STRIP_MB, CLIBD_JSPLIT_MAX,
+// CLIBD_BWD_TWO_SWEEPS, CLIBD_BWD_SINGLE).  They shape the scratch layout, so the forward snapshots them per scratch
+// pointer and the later phases of the same step (finish, backward) reuse that snapshot: an environment change between
+// a forward and its backward cannot shift the offsets under the backward's feet.
+struct PlanKnobs {
+    int64_t shared_min_n = 4096;
+    double strip_mb = 2304.0;
+    int64_t js_cap = 8;
+    bool two_sweeps = false;
+    bool bwd_single = false;
+};
+PlanKnobs plan_knobs_from_env();
+void remember_plan_knobs(const void* scratch, const PlanKnobs& k);
+PlanKnobs plan_knobs_for(const void* scratch);  // the forward's snapshot, else the environment
+LossPlan make_loss_plan(int64_t N, int64_t n_local, int64_t d, int path, bool allow_shared_s = true, int mode = 0,
+                        const PlanKnobs* knobs = nullptr);
 
 template <typename T>
 inline T* at(void* base, size_t off) {
@@ -180,6 +196,8 @@ struct NormBwdArgs {
     float* dots;            // [n]
 };
 int launch_normalize_bwd(const NormBwdArgs& a, cudaStream_t s);
+// up to three modalities (same n, dtype) in one launch
+int launch_normalize_bwd_multi(const NormBwdArgs* args, int count, cudaStream_t s);
 
 // ---- CUDA-core fp32 path (loss_simt.cu) ---------------------------------------------
 int simt_forward_pair(const void* xa, const void* xb, int dtype, const float* inv_a, const float* inv_b, int64_t N,

@@ -224,16 +224,18 @@ struct JobList {
 };
 
 // Batched form of the class sums: one warp per (CS_SPAN consecutive sorted positions, 256-column chunk) handles every
-// class segment whose HEAD lies in its span (about one class of 8 at the benchmark's label distribution), so every warp
-// of the grid carries work -- with one warp per position seven of eight exit at once and an SM is left with a handful
-// of loads in flight (measured: 35 us per 50 MB modality, 1.4 TB/s).  Four members' 16-byte loads are in flight per
-// lane, and up to two differently weighted sums of the same rows are formed per pass (the lam2-weighted class sums of
-// the image rows for the pairs (image, dna) and (image, text) read the rows once).  Members are added in index order.
+// class segment whose HEAD lies in its span (about one class of 8 at the benchmark's label distribution).  What made
+// the first versions slow was latency, not bytes (35-42 us per 50 MB modality = 1.4 TB/s): a warp per position leaves
+// seven of eight warps with nothing to do, and a serial scan of the span or a one-row-at-a-time member loop is a chain
+// of dependent global loads.  Here the span's nine keys are fetched by nine lanes at once (heads by ballot), four
+// members' 16-byte loads are in flight per lane, and the second weighted sum (the lam2-weighted class sums of the
+// image rows for the pairs (image, dna) and (image, text) share one pass) is a template switch so that the common
+// one-sum case keeps its registers -- and its occupancy.  Members are added in index order (fixed summation order).
 constexpr int CS_SPAN = 8;
-template <typename T>
-__global__ void class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t* __restrict__ skey,
-                                       const int32_t* __restrict__ sidx, const float* __restrict__ cnt, int64_t N,
-                                       int64_t d, int64_t row0, int64_t n, int nchunks) {
+template <typename T, bool TWO>
+__global__ void __launch_bounds__(kThreads)
+class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t* __restrict__ skey, const int32_t* __restrict__ sidx,
+                       const float* __restrict__ cnt, int64_t N, int64_t d, int64_t row0, int64_t n, int nchunks) {
     const ClassSumJob& jb = jobs.j[blockIdx.y];
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -241,12 +243,20 @@ __global__ void class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t*
     const int chunk = static_cast<int>(item - span * nchunks);
     const int64_t p0 = span * CS_SPAN;
     if (p0 >= N) return;
+    // lane l in [0, CS_SPAN] holds the key of sorted position p0 - 1 + l (-1 before the first position)
+    const int64_t pidx = p0 - 1 + lane;
+    int32_t key = -1;
+    if (lane <= CS_SPAN && pidx >= 0 && pidx < N) key = skey[pidx];
+    const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool is_head = lane >= 1 && lane <= CS_SPAN && pidx < N && key != prev;
+    unsigned heads = __ballot_sync(0xffffffffu, is_head);
     const int64_t c = static_cast<int64_t>(chunk) * 256 + lane * 8;
     const T* x = static_cast<const T*>(jb.x);
-    const bool two = jb.out[1] != nullptr;
-    for (int64_t p = p0; p < p0 + CS_SPAN && p < N; ++p) {
-        const int32_t r = skey[p];
-        if (p > 0 && skey[p - 1] == r) continue;  // not the head of its segment
+    while (heads != 0u) {
+        const int hl = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int64_t p = p0 - 1 + hl;
+        const int32_t r = __shfl_sync(0xffffffffu, key, hl);
         const int members = static_cast<int>(cnt[r]);
         if (n < N) {  // row-sharded: only classes with a member among the local rows are ever read on this rank
             bool need = false;
@@ -258,7 +268,11 @@ __global__ void class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t*
         }
         if (c >= d) continue;
         float acc0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float acc1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float acc1[TWO ? 8 : 1] = {0.f};
+        if (TWO) {
+#pragma unroll
+            for (int k = 0; k < (TWO ? 8 : 1); ++k) acc1[k] = 0.f;
+        }
         for (int m0 = 0; m0 < members; m0 += 4) {
             float v[4][8], w0[4], w1[4];
 #pragma unroll
@@ -268,7 +282,7 @@ __global__ void class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t*
                     const int64_t j = sidx[p + m0 + u];
                     const float iv = jb.inv[j];
                     w0[u] = iv * (jb.lam2[0] ? 1.f - 0.5f * jb.lam2[0][j] : 1.f);
-                    if (two) w1[u] = iv * (jb.lam2[1] ? 1.f - 0.5f * jb.lam2[1][j] : 1.f);
+                    if (TWO) w1[u] = iv * (jb.lam2[1] ? 1.f - 0.5f * jb.lam2[1][j] : 1.f);
                     load8(x + j * d + c, v[u]);
                 } else {
 #pragma unroll
@@ -280,12 +294,17 @@ __global__ void class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t*
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     acc0[k] += v[u][k] * w0[u];
-                    acc1[k] += v[u][k] * w1[u];
+                    if (TWO) acc1[k] += v[u][k] * w1[u];
                 }
             }
         }
         store8(jb.out[0] + static_cast<int64_t>(r) * d + c, acc0);
-        if (two) store8(jb.out[1] + static_cast<int64_t>(r) * d + c, acc1);
+        if (TWO) {
+            float a1[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a1[k] = acc1[TWO ? k : 0];
+            store8(jb.out[1] + static_cast<int64_t>(r) * d + c, a1);
+        }
     }
 }
 
@@ -565,8 +584,13 @@ __global__ void loss_finish_stage2_kernel(int64_t N, float scale, float w0, floa
 // One warp per local row: dxhat = (scale/N) * (sum_splits dxh - 2 * sum_partners w_p Q_partner[rep]),
 // dots = xhat . dxhat, dx = grad_scale * (dxhat - xhat * dots) / ||x||.  Rows up to 1024 columns stay in
 // registers between the dot product and the projection (one pass over HBM).
+struct NormBwdList {
+    NormBwdArgs a[3];
+};
+
 template <typename T, bool VEC>
-__global__ void normalize_bwd_kernel(NormBwdArgs a) {
+__global__ void normalize_bwd_kernel(NormBwdList list) {
+    const NormBwdArgs& a = list.a[blockIdx.y];  // blockIdx.y = modality: all of them in one launch
     const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= a.n) return;
@@ -868,8 +892,25 @@ int launch_class_sums_jobs(const ClassSumJob* jobs, int njobs, int dtype, const 
     }
     const int nchunks = static_cast<int>(ceil_div(d, 256));
     dim3 grid(static_cast<unsigned>(ceil_div(ceil_div(N, CS_SPAN) * nchunks * 32, kThreads)), static_cast<unsigned>(njobs));
+    // a launch forms two sums per job only when some job asks for it; the others then get a second, unused target
+    bool two = false;
+    for (int i = 0; i < njobs; ++i) two = two || jobs[i].out[1] != nullptr;
+    if (two) {  // jobs with one target run in their own one-sum launch (fewer registers, higher occupancy)
+        ClassSumJob one[MAX_JOBS], both[MAX_JOBS];
+        int n1 = 0, n2 = 0;
+        for (int i = 0; i < njobs; ++i) (jobs[i].out[1] ? both[n2++] : one[n1++]) = jobs[i];
+        if (n1 > 0) {
+            int rc = launch_class_sums_jobs(one, n1, dtype, skey, sidx, cnt, N, d, row0, n, s);
+            if (rc) return rc;
+        }
+        dim3 grid2(grid.x, static_cast<unsigned>(n2));
+        const JobList<ClassSumJob> l2 = job_list(both, n2);
+        DISPATCH_DTYPE(dtype, (class_sums_jobs_kernel<T, true><<<grid2, kThreads, 0, s>>>(l2, skey, sidx, cnt, N, d, row0, n, nchunks)));
+        CLIBD_KERNEL_CHECK();
+        return 0;
+    }
     const JobList<ClassSumJob> l = job_list(jobs, njobs);
-    DISPATCH_DTYPE(dtype, (class_sums_jobs_kernel<T><<<grid, kThreads, 0, s>>>(l, skey, sidx, cnt, N, d, row0, n, nchunks)));
+    DISPATCH_DTYPE(dtype, (class_sums_jobs_kernel<T, false><<<grid, kThreads, 0, s>>>(l, skey, sidx, cnt, N, d, row0, n, nchunks)));
     CLIBD_KERNEL_CHECK();
     return 0;
 }
@@ -923,20 +964,29 @@ int launch_sweep_prep_jobs(const SweepPrepJob* jobs, int njobs, const int32_t* s
     return 0;
 }
 
-int launch_normalize_bwd(const NormBwdArgs& a_in, cudaStream_t s) {
-    if (a_in.n == 0) return 0;
-    NormBwdArgs a = a_in;
-    a.scale_dev = scale_dev_ptr();
-    const int64_t blocks = ceil_div(a.n * 32, kThreads);
-    bool vec = rows_vec8_ok<void>(a.x, a.d) && (a.jsplit == 0 || rows_vec8_ok<void>(a.dxh, a.d)) &&
-               (a.extra_slots == 0 || rows_vec8_ok<void>(a.extra, a.d)) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
-    for (int p = 0; p < 2; ++p)
-        if (a.Qp[p]) vec = vec && rows_vec8_ok<void>(a.Qp[p], a.d);
-    DISPATCH_DTYPE(a.dtype, {
+int launch_normalize_bwd(const NormBwdArgs& a_in, cudaStream_t s) { return launch_normalize_bwd_multi(&a_in, 1, s); }
+
+int launch_normalize_bwd_multi(const NormBwdArgs* args, int count, cudaStream_t s) {
+    if (count == 0 || args[0].n == 0) return 0;
+    CLIBD_REQUIRE(count <= 3, "at most three modalities");
+    NormBwdList list;
+    bool vec = true;
+    for (int m = 0; m < count; ++m) {
+        NormBwdArgs& a = list.a[m];
+        a = args[m];
+        CLIBD_REQUIRE(a.n == args[0].n && a.dtype == args[0].dtype, "modalities of one launch share shape and dtype");
+        a.scale_dev = scale_dev_ptr();
+        vec = vec && rows_vec8_ok<void>(a.x, a.d) && (a.jsplit == 0 || rows_vec8_ok<void>(a.dxh, a.d)) &&
+              (a.extra_slots == 0 || rows_vec8_ok<void>(a.extra, a.d)) && (a.dx == nullptr || rows_vec8_ok<void>(a.dx, a.d));
+        for (int p = 0; p < 2; ++p)
+            if (a.Qp[p]) vec = vec && rows_vec8_ok<void>(a.Qp[p], a.d);
+    }
+    dim3 grid(static_cast<unsigned>(ceil_div(args[0].n * 32, kThreads)), static_cast<unsigned>(count));
+    DISPATCH_DTYPE(args[0].dtype, {
         if (vec)
-            normalize_bwd_kernel<T, true><<<blocks, kThreads, 0, s>>>(a);
+            normalize_bwd_kernel<T, true><<<grid, kThreads, 0, s>>>(list);
         else
-            normalize_bwd_kernel<T, false><<<blocks, kThreads, 0, s>>>(a);
+            normalize_bwd_kernel<T, false><<<grid, kThreads, 0, s>>>(list);
     });
     CLIBD_KERNEL_CHECK();
     return 0;

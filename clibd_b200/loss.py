@@ -103,15 +103,33 @@ def _device_ctx(device):
     return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
 
 
-def _coalesced(group):
-    """One NCCL launch for a batch of same-kind collectives (torch's coalescing manager batches
-    all_gather_into_tensor / all_reduce calls into a single grouped call); plain sequential calls elsewhere."""
+def _gather_rows(local, labels, gathered, all_labels, group):
+    """All-gather of the labels (their own dtype) and of every present feature set.  On NCCL the feature gathers are
+    batched into one grouped launch through torch's coalescing manager when that (private) API is there and can be entered;
+    otherwise they run as plain sequential collectives -- same result."""
+    dist.all_gather_into_tensor(all_labels, labels, group=group)  # int64, on its own: a grouped call wants one dtype
+
+    def issue():
+        for f, g in zip(local, gathered):
+            if f is not None:
+                dist.all_gather_into_tensor(g, f, group=group)
+
+    manager = None
     try:
         if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
-            return dist._coalescing_manager(group=group)
+            manager = dist._coalescing_manager(group=group)
+            manager.__enter__()
     except Exception:  # noqa: BLE001
-        pass
-    return contextlib.nullcontext()
+        manager = None
+    if manager is None:
+        issue()
+        return
+    try:
+        issue()
+    except BaseException as ex:
+        manager.__exit__(type(ex), ex, ex.__traceback__)
+        raise
+    manager.__exit__(None, None, None)
 
 
 def _shard_mode(path, d, group, device):
@@ -218,13 +236,8 @@ class _FusedClipLossFn(torch.autograd.Function):
                 if world > 1:
                     all_labels = torch.empty(N, dtype=torch.int64, device=device)
                     gathered = [None if f is None else torch.empty((N, d), dtype=dtype, device=device) for f in local]
-                    # labels + up to three feature sets in ONE grouped all-gather; a coalesced call wants one dtype, and
-                    # an all-gather only concatenates bytes, so the int64 labels travel viewed as the feature dtype
-                    with _coalesced(group):
-                        dist.all_gather_into_tensor(all_labels.view(dtype), labels.view(dtype), group=group)
-                        for f, g in zip(local, gathered):
-                            if f is not None:
-                                dist.all_gather_into_tensor(g, f, group=group)
+                    # labels + up to three feature sets in one grouped all-gather where NCCL coalescing is available
+                    _gather_rows(local, labels, gathered, all_labels, group)
                     # inverse norms of all rows from the gathered features: one 50 MB read per modality instead of
                     # one more latency-bound collective each
                     inv = [None if g is None else inv_norms(g) for g in gathered]
@@ -248,6 +261,10 @@ class _FusedClipLossFn(torch.autograd.Function):
                                                          st, st + 12 * N, pos.data_ptr(), loss.data_ptr(), stream))
                 ctx.keep = (gathered, inv, stats)
                 ctx.x_ptrs, ctx.inv_ptrs, ctx.posrow_ptr = gathered_ptrs, inv_ptrs, st + 24 * N
+                if world == 1:
+                    # the backward re-reads the inputs: saving them lets autograd's version counters catch an in-place
+                    # modification between forward and backward (the kernels read through the pointers kept above)
+                    ctx.save_for_backward(*[f for f in feats if f is not None])
         ctx.scratch = scratch
         ctx.meta = (N, n, d, row0, scale_value, tuple(weights), path, group, world, rank, dtype, device, sum_grads, shard)
         ctx.has_scale = scale_tensor is not None
@@ -259,6 +276,7 @@ class _FusedClipLossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         lib = _lib.load()
         N, n, d, row0, scale_value, weights, path, group, world, rank, dtype, device, sum_grads, shard = ctx.meta
+        _ = ctx.saved_tensors  # raises if a saved input was modified in place since the forward
         stream = _stream_ptr(device)
         with _device_ctx(device):
             grad_out = grad_out.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()

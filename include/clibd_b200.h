@@ -105,7 +105,7 @@ int clibd_loss_forward_finish(int64_t n_global, int64_t n_local, int64_t d, floa
  * multiply by the rank's own grad_output).  grad_feat_scale = sum over ranks of
  * grad_output (the reduce-scatter(SUM) convention of torch.distributed.nn.all_gather,
  * loss_func.py:97).  The scale used is the one clibd_loss_forward_stats stored in the scratch (logit_scale here is
- * informational).  With n_local == n_global (one GPU) and n_global >= 6144 the backward computes S once per
+ * informational).  With n_local == n_global (one GPU) and n_global >= 4096 the backward computes S once per
  * modality pair and passes its 16-bit coefficients to a second GEMM through a strip inside the scratch
  * (environment: CLIBD_GT_STRIP_MB bounds the strip, CLIBD_BWD_TWO_SWEEPS=1 selects the two-sweep form).
  * This one-call form is for one GPU and for mode 0; mode 1 uses the two calls below. */

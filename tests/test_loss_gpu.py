@@ -69,7 +69,7 @@ def _synthetic(N, d, nmod, labels_kind, seed, dtype):
 @pytest.fixture(params=["two_sweeps", "shared_s"])
 def backward_form(request, monkeypatch):
     """Both backward forms at oracle-sized batches: the two-sweep form (what small batches and sharded jobs run)
-    and the single-GPU form that computes S once per pair (normally taken from N = 6144 up)."""
+    and the single-GPU form that computes S once per pair (normally taken from N = 4096 up)."""
     if request.param == "shared_s":
         monkeypatch.setenv("CLIBD_SHARED_S_MIN_N", "1")
     else:
@@ -302,7 +302,7 @@ def test_errors_and_edge_cases():
 @pytest.mark.parametrize("N", [4096, 32768])
 def test_benchmarked_configurations_match_the_float64_oracle(N):
     """BASELINE config 2 (N = 4096) and the benchmarked north-star configuration (N = 32768): three modalities, bf16
-    values, labels ~ randint(0, N/8), the backward form bench.py times (S once per pair from N = 6144 up) -- against
+    values, labels ~ randint(0, N/8), the backward form bench.py times (S once per pair from N = 4096 up) -- against
     values the float64 streaming oracle produced for the SAME seeded batch (tools/synth.py, oracle/
     gen_golden_fullsize.py; 192 s of host time at N = 32768, so the oracle ran once and its results are stored):
     loss, dL/d(logit_scale) and the gradient rows of three 32-row blocks (first, middle, last) of every modality,
