@@ -73,6 +73,50 @@ cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
     return e;
 }
 
+// A second stream per device (and per role: forward / backward) on which HBM-bound staging work runs NEXT TO the tensor
+// kernels: the forward and gradient-GEMM kernels leave registers (104 / 102 per thread x 384 threads) and issue slots for
+// a 256-thread block without shared memory, and a sweep of a sharded step leaves whole SMs idle.  Fork / join by events,
+// which is also the legal pattern inside a stream capture (graph_cache.cu).  CLIBD_SIDE_STREAM=0 runs everything in line.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream(int role) {
+    static std::mutex mu;
+    static SideStream table[64][2];
+    const char* e = std::getenv("CLIBD_SIDE_STREAM");  // read per call: tools/ab_step.py flips it inside one process
+    if (e != nullptr && std::atoi(e) == 0) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    SideStream& st = table[dev][role];
+    if (st.stream == nullptr) {
+        cudaStream_t s = nullptr;
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        st.stream = s;
+        st.fork = a;
+        st.join = b;
+    }
+    return &st;
+}
+// fork: everything enqueued on `main` so far happens before the side work; join: `main` waits for the side work
+static int side_fork(SideStream* ss, cudaStream_t main) {
+    CLIBD_CHECK_CUDA(cudaEventRecord(ss->fork, main));
+    CLIBD_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    return 0;
+}
+static int side_join(SideStream* ss, cudaStream_t main) {
+    CLIBD_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
+    CLIBD_CHECK_CUDA(cudaStreamWaitEvent(main, ss->join, 0));
+    return 0;
+}
+
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 PlanKnobs plan_knobs_from_env() {
@@ -311,6 +355,7 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
     const int32_t* class_lo = at<int32_t>(scratch, plan.off_class_lo);
     void* gt = at<void>(scratch, plan.off_gt);
     int rc = 0;
+    SideStream* side = nullptr;
     bool wrote_dxh[3] = {false, false, false};
     bool wrote_part[3] = {false, false, false};
     // Per pair: the column coefficients in class-sorted order (ccS) and lam2 of every row the weighted class sums Qw
@@ -347,7 +392,12 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
             }
         }
         if ((rc = launch_sweep_prep_jobs(sp, nsp, sidx, cnt, N, 0, N, logit_scale, stream))) return rc;
-        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, skey, sidx, cnt, N, d, row0, n, stream))) return rc;
+        // the weighted class sums are read by the normalise-backward pass only: they run on the side stream next to the
+        // sweeps (a sharded sweep leaves SMs idle) and the gradient GEMMs, and are joined at the end of this function
+        side = side_stream(1);
+        if (side != nullptr && (rc = side_fork(side, stream))) return rc;
+        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, skey, sidx, cnt, N, d, row0, n, side ? side->stream : stream)))
+            return rc;
     }
     // Pairs are processed in groups that share their column modality b: (image, dna) -> dna; (image, text) and
     // (dna, text) -> text.  Every pair of a group sweeps its rows into its own coefficient strip, then ONE gradient
@@ -357,8 +407,12 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
     int ngroups = 0;
     for (int p = 0; p < 3; ++p) {
         if (pair_weight[p] == 0.f) continue;
+        // Merged only in the sharded step, where K = n local rows per pair is short and the merge saves a trip over
+        // NVLink.  On one GPU a K range of 2 N rows lets the three pairs of CTAs that share a strip block (one per
+        // 256-column feature tile) drift apart until L2 no longer serves the re-reads: ncu showed 12.1 GB of DRAM reads
+        // for the merged launch against 2 x 3.7 GB for two launches, and 2.70 ms against 2 x 1.21 ms.
         int g = -1;
-        for (int k = 0; k < ngroups; ++k)
+        for (int k = 0; k < ngroups && plan.exchange; ++k)
             if (group_size[k] == 1 && kPairB[group_pairs[k][0]] == kPairB[p] && pair_weight[group_pairs[k][0]] == pair_weight[p])
                 g = k;
         if (g < 0) g = ngroups++;
@@ -417,6 +471,7 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
         if (!plan.exchange) wrote_dxh[b] = true;
         else wrote_part[b] = true;
     }
+    if (side != nullptr && (rc = side_join(side, stream))) return rc;
     return 0;
 }
 
@@ -587,34 +642,54 @@ static int loss_forward_stats_impl(const void* const x[3], int dtype, const floa
     }
     // class sums Q[m] feed the positive term of the partner's rows: every pair's second modality, and the first one too
     // when both directions are swept (S once per pair: the column side's target term uses the lam2-weighted Qw)
-    {
-        ClassSumJob cj[3];
-        int ncj = 0;
-        for (int m = 0; m < 3; ++m) {
-            if (!used[m] || !col_op[m]) continue;
-            cj[ncj].x = x[m];
-            cj[ncj].inv = inv_norm[m];
-            cj[ncj].out[0] = at<float>(scratch, plan.off_Q[m]);
-            ++ncj;
-        }
-        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, ls.skey, ls.sidx, cnt, N, d, row0, n, stream))) return rc;
-    }
+    ClassSumJob cj[3];
+    int ncj = 0;
     for (int m = 0; m < 3; ++m) {
-        if (!used[m]) continue;
-        if (!tc) continue;
-        if (col_op[m] &&
-            (rc = launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16, nullptr,
-                                       at<void>(scratch, plan.off_xhT[m]), stream, ls.sidx,
-                                       at<void>(scratch, plan.off_xhS[m]))))
-            return rc;
-        if (row_op[m]) {
-            const size_t esize = dtype == DT_F32 ? 4 : 2;
-            const void* xl = static_cast<const char*>(x[m]) + static_cast<size_t>(row0) * d * esize;
-            void* xh_loc = at<char>(scratch, plan.off_xh[m]) + static_cast<size_t>(row0) * plan.dpad * 2;
-            if ((rc = launch_make_operands(xl, dtype, inv_norm[m] + row0, n, d, plan.dpad, plan.npad_loc, fmt_bf16, xh_loc,
-                                           plan.shared_s ? at<void>(scratch, plan.off_xhTo[m]) : nullptr, stream)))
-                return rc;
+        if (!used[m] || !col_op[m]) continue;
+        cj[ncj].x = x[m];
+        cj[ncj].inv = inv_norm[m];
+        cj[ncj].out[0] = at<float>(scratch, plan.off_Q[m]);
+        ++ncj;
+    }
+    // staging tasks: (modality, column operands) and (modality, row operand of the local rows)
+    auto stage_col = [&](int m, cudaStream_t st) -> int {
+        return launch_make_operands(x[m], dtype, inv_norm[m], N, d, plan.dpad, plan.npad, fmt_bf16, nullptr,
+                                    at<void>(scratch, plan.off_xhT[m]), st, ls.sidx, at<void>(scratch, plan.off_xhS[m]));
+    };
+    auto stage_row = [&](int m, cudaStream_t st) -> int {
+        const size_t esize = dtype == DT_F32 ? 4 : 2;
+        const void* xl = static_cast<const char*>(x[m]) + static_cast<size_t>(row0) * d * esize;
+        void* xh_loc = at<char>(scratch, plan.off_xh[m]) + static_cast<size_t>(row0) * plan.dpad * 2;
+        return launch_make_operands(xl, dtype, inv_norm[m] + row0, n, d, plan.dpad, plan.npad_loc, fmt_bf16, xh_loc,
+                                    plan.shared_s ? at<void>(scratch, plan.off_xhTo[m]) : nullptr, st);
+    };
+    // The first weighted pair's operands are staged on the caller's stream and its forward kernel starts; everything
+    // else -- the class sums and the other modalities' operand copies -- runs on the side stream next to that kernel
+    // and is joined before the second pair.
+    int first_pair = -1;
+    for (int p = 0; p < 3 && first_pair < 0; ++p)
+        if (pair_weight[p] != 0.f) first_pair = p;
+    SideStream* side = (tc && first_pair >= 0) ? side_stream(0) : nullptr;
+    bool side_pending = false;
+    if (tc) {
+        bool done_row[3] = {false, false, false}, done_col[3] = {false, false, false};
+        if (side != nullptr) {
+            const int a0 = kPairA[first_pair], b0 = kPairB[first_pair];
+            if ((rc = side_fork(side, stream))) return rc;
+            if ((rc = stage_row(a0, stream))) return rc;
+            if ((rc = stage_col(b0, stream))) return rc;
+            done_row[a0] = done_col[b0] = true;
+            side_pending = true;
         }
+        cudaStream_t st2 = side ? side->stream : stream;
+        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, ls.skey, ls.sidx, cnt, N, d, row0, n, st2))) return rc;
+        for (int m = 0; m < 3; ++m) {
+            if (!used[m]) continue;
+            if (col_op[m] && !done_col[m] && (rc = stage_col(m, st2))) return rc;
+            if (row_op[m] && !done_row[m] && (rc = stage_row(m, st2))) return rc;
+        }
+    } else {
+        if ((rc = launch_class_sums_jobs(cj, ncj, dtype, ls.skey, ls.sidx, cnt, N, d, row0, n, stream))) return rc;
     }
     float* posrow2 = at<float>(scratch, plan.off_posrow2);
     double* red = at<double>(scratch, plan.off_red);
@@ -646,6 +721,10 @@ static int loss_forward_stats_impl(const void* const x[3], int dtype, const floa
                                    colpart, stream);
         }
         if (rc) return rc;
+        if (side_pending) {  // the other pairs' operands and the class sums must be there from here on
+            if ((rc = side_join(side, stream))) return rc;
+            side_pending = false;
+        }
         rj[nrj].part = rowpart;
         rj[nrj].parts = plan.row_parts;
         rj[nrj].stride = n;
@@ -880,6 +959,8 @@ static GraphKey base_key(int tag, const void* const x[3], int dtype, const float
     const PlanKnobs knobs = tag == 1 ? plan_knobs_from_env() : plan_knobs_for(scratch);
     const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
     k.add(plan.total).add(plan.jsplit).add(plan.shared_s).add(plan.strip_rows).add(plan.bwd_single);
+    const char* side_env = std::getenv("CLIBD_SIDE_STREAM");
+    k.add(side_env != nullptr && std::atoi(side_env) == 0);  // the captured sequence forks a side stream or does not
     return k;
 }
 

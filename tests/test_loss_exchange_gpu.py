@@ -201,3 +201,23 @@ def test_simulated_ranks_trained_regime():
         assert abs(losses[0] - ref["loss"]) <= 1e-3 * max(abs(ref["loss"]), scale)
         for i in range(3):
             assert _rel(grads[i], world * ref["grads"][i]) < 6e-3, (form, i)
+
+
+def test_side_stream_overlap_is_bit_identical(monkeypatch):
+    """Staging work that runs on the library's side stream next to the tensor kernels (class sums, the operand copies
+    of the later pairs; fork / join by events, csrc/loss_api.cu) must not change a single bit: the same sharded step
+    with CLIBD_SIDE_STREAM=0 (everything in line) and =1, repeated -- a missing dependency shows up as a mismatch."""
+    from clibd_b200 import _lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    N, d, world = 2048, 768, 4
+    feats = [torch.randn(N, d, generator=gen).bfloat16().to(dev) for _ in range(3)]
+    labels = torch.randint(0, N // 8, (N,), generator=gen).to(dev)
+    monkeypatch.setenv("CLIBD_SIDE_STREAM", "0")
+    ref = _sharded_step(feats, labels, 1 / 0.07, world, _lib.PATH_TC_BF16, "peer")
+    for rep in range(3):
+        monkeypatch.setenv("CLIBD_SIDE_STREAM", "1")
+        got = _sharded_step(feats, labels, 1 / 0.07, world, _lib.PATH_TC_BF16, "peer")
+        assert got[0] == ref[0] and got[2] == ref[2]
+        for a, b in zip(got[1], ref[1]):
+            assert np.array_equal(a, b)

@@ -350,3 +350,23 @@ def test_default_path_for_float32_inputs():
     for i in range(3):
         assert _rel(grads[i], ref["grads"][i]) < 2e-4, i
     assert abs(ds - ref["dlogit_scale"]) <= 2e-4 * abs(ref["dlogit_scale"])
+
+
+def test_side_stream_overlap_is_bit_identical_single_gpu(monkeypatch):
+    """One GPU, S once per pair (N = 4096): the step with the staging work on the side stream equals the in-line step
+    bit for bit (loss, gradients, dlogit_scale), run after run."""
+    import clibd_b200 as cb
+    dev = torch.device("cuda:0")
+    feats, labels = _synthetic(4096, 768, 3, "multi", seed=5, dtype=torch.bfloat16)
+    feats = [f.to(dev) for f in feats]
+    labels = labels.to(dev)
+    scale = torch.tensor(1 / 0.07, device=dev)
+    mod = cb.ContrastiveLoss(None, 1 / 0.07)
+    monkeypatch.setenv("CLIBD_SIDE_STREAM", "0")
+    ref = _run(mod, feats, labels, scale)
+    monkeypatch.setenv("CLIBD_SIDE_STREAM", "1")
+    for rep in range(4):
+        got = _run(mod, feats, labels, scale)
+        assert got[0] == ref[0] and got[2] == ref[2]
+        for a, b in zip(got[1], ref[1]):
+            assert np.array_equal(a, b)

@@ -31,16 +31,15 @@ def main():
     md = [f"# ncu --set full --clock-control none summaries ({tag})",
           "Times under ncu are cold-cache and serialised; use shares, not absolutes.", ""]
     traffic = {}
+    per_kernel = {}
     for rep in reps:
         hdr, units, data = rows(rep)
         ki = hdr.index("Kernel Name")
-        seen = set()
+        count = {}
         for r in data:
             name = r[ki].split("(")[0].split("::")[-1]
-            if name in seen:
-                continue
-            seen.add(name)
-            md += [f"## {name}  ({os.path.basename(rep)})", "", "| metric | value | unit |", "|---|---|---|"]
+            count[name] = count.get(name, 0) + 1
+            md += [f"## {name}  launch {count[name]}  ({os.path.basename(rep)})", "", "| metric | value | unit |", "|---|---|---|"]
             tot = 0.0
             for m in METRICS:
                 if m in hdr:
@@ -49,13 +48,14 @@ def main():
                     if m.startswith("dram__bytes_"):
                         tot += float(r[i].replace(",", "")) * UNIT_SCALE.get(units[i], 1.0)
             md.append("")
-            traffic[name.split("<")[0]] = int(tot)
+            per_kernel.setdefault(name.split("<")[0], []).append(tot)
+    traffic = {k: int(sum(v) / len(v)) for k, v in per_kernel.items()}  # mean over the captured launches of a kernel
     open(os.path.join(root, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(md))
     tj_path = os.path.join(root, "profiles", "dram_traffic.json")
     tj = json.load(open(tj_path))
     for k, v in traffic.items():
         if k.startswith("loss_"):
-            tj[k] = {"config": "N=32768 d=768 n_gpus=1", "bytes_per_launch": v, "source": f"gpurun_out/prof_loss_{tag}.ncu-rep"}
+            tj[k] = {"config": "N=32768 d=768 n_gpus=1", "bytes_per_launch": v, "source": f"gpurun_out/prof_loss_{tag}.ncu-rep (mean over the captured launches of one step)"}
     json.dump(tj, open(tj_path, "w"), indent=1)
     print("\n".join(md))
 
