@@ -32,6 +32,7 @@ SIGNATURES = {
     "clibd_loss_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
     "clibd_loss_forward_stats": (_INT, [_P, _INT, _P, _P, _I64, _I64, _I64, _I64, _F, _P, _P, _INT, _INT, _P, _I64, _P,
                                         _P, _P, _P, _P]),
+    "clibd_loss_label_stage": (_INT, [_P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P]),
     "clibd_loss_forward_finish": (_INT, [_I64, _I64, _I64, _F, _P, _INT, _INT, _P, _I64, _P, _P, _P, _P, _P]),
     "clibd_loss_backward": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _F, _P, _P, _P, _P]),
     "clibd_loss_backward_sweeps": (_INT, [_P, _INT, _P, _I64, _I64, _I64, _I64, _F, _P, _INT, _P, _I64, _P, _P, _P,

@@ -95,6 +95,7 @@ class PeerContext:
         self.N, self.n, self.d, self.world, self.rank = N, n, d, world, rank
         self.esize = torch.empty((), dtype=dtype).element_size()
         self.entries = []
+        self._side = None
         self._next = 0
         self._parity = 1
         self.red_pair_bytes = 4 * world * n * d  # one pair's slot array [W, n, d]
@@ -109,10 +110,16 @@ class PeerContext:
                                          for q in range(world) for p in range(3)]) for par in range(2)]
         self.peer_gslots = [_lib.ptr_array([base[q] + g_off + par * 256 for q in range(world)]) for par in range(2)]
 
-    def barrier(self):
+    def barrier(self, channel=0):
         """All ranks' earlier work on the current stream (incl. their stores into peer memory) is complete and visible
-        before any rank's later work starts."""
-        self.shared.handle.barrier()
+        before any rank's later work starts.  Barriers issued on two streams at once use different channels."""
+        self.shared.handle.barrier(channel=channel)
+
+    def side_stream(self):
+        """Second stream of the forward: the push of the feature rows runs there, next to the label statistics."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def acquire(self) -> Entry:
         k = len(self.entries)

@@ -588,12 +588,12 @@ static int loss_forward_stats_impl(const void* const x[3], int dtype, const floa
                              int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
                              float* posrow_out, double* pos, clibd_stream_t stream) {
     CLIBD_REQUIRE(mode == LOSS_MODE_LOCAL || mode == LOSS_MODE_EXCHANGE, "mode must be 0 or 1");
-    const PlanKnobs knobs = plan_knobs_from_env();
+    const PlanKnobs knobs = labels != nullptr ? plan_knobs_from_env() : plan_knobs_for(scratch);
     remember_plan_knobs(scratch, knobs);  // finish / backward of this step lay the scratch out the same way
     const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
     int rc = check_common(x, inv_norm, pair_weight, N, d, row0, n, dtype, path, scratch, scratch_bytes, plan);
     if (rc) return rc;
-    CLIBD_REQUIRE(labels && rowsum && colsum && pos, "null output pointer");
+    CLIBD_REQUIRE(rowsum && colsum && pos, "null output pointer");  // labels == null: clibd_loss_label_stage ran already
     if (mode == LOSS_MODE_EXCHANGE && n < N) {
         CLIBD_REQUIRE(plan.exchange, "exchange mode needs a tensor-core path and a feature dim <= 768");
         CLIBD_REQUIRE(posrow_out != nullptr, "exchange mode needs the posrow output");
@@ -620,11 +620,13 @@ static int loss_forward_stats_impl(const void* const x[3], int dtype, const floa
     ls.iota = at<int32_t>(scratch, plan.off_iota);
     ls.sort_tmp = at<void>(scratch, plan.off_sorttmp);
     ls.sort_tmp_bytes = plan.sort_tmp_bytes;
-    if ((rc = launch_label_stats(labels, N, rep, cnt, ls, stream))) return rc;
-    if ((rc = launch_gscale(cnt, N, path, gscale, stream))) return rc;
-    if ((rc = launch_class_ranges(ls.skey, rep, N, at<int32_t>(scratch, plan.off_cstart),
-                                  at<int32_t>(scratch, plan.off_class_lo), stream)))
-        return rc;
+    if (labels != nullptr) {
+        if ((rc = launch_label_stats(labels, N, rep, cnt, ls, stream))) return rc;
+        if ((rc = launch_gscale(cnt, N, path, gscale, stream))) return rc;
+        if ((rc = launch_class_ranges(ls.skey, rep, N, at<int32_t>(scratch, plan.off_cstart),
+                                      at<int32_t>(scratch, plan.off_class_lo), stream)))
+            return rc;
+    }
     bool used[3] = {false, false, false};
     for (int p = 0; p < 3; ++p)
         if (pair_weight[p] != 0.f) used[kPairA[p]] = used[kPairB[p]] = true;
@@ -948,6 +950,35 @@ static int loss_backward_finish_impl(const void* const x[3], int dtype, const fl
                            reduced_slots, grad_feat_scale, grad_feat_scale_dev, grad_count, dx, dscale_partial, stream);
 }
 
+// Label statistics alone (representatives, class sizes, class sort, ranges): everything the forward derives from the
+// labels and nothing else.  A sharded step runs it as soon as the labels have arrived, next to the push of the feature
+// rows, and then calls clibd_loss_forward_stats with labels == NULL.
+static int loss_label_stage_impl(const int64_t* labels, int64_t N, int64_t n, int64_t d, int path, int mode, void* scratch,
+                                 int64_t scratch_bytes, cudaStream_t stream) {
+    CLIBD_REQUIRE(labels != nullptr && N > 0 && n >= 0 && d > 0 && path >= 0 && path <= 2 && mode >= 0 && mode <= 1,
+                  "bad arguments");
+    const PlanKnobs knobs = plan_knobs_from_env();
+    remember_plan_knobs(scratch, knobs);
+    const LossPlan plan = make_loss_plan(N, n, d, path, true, mode, &knobs);
+    CLIBD_REQUIRE(scratch && scratch_bytes >= static_cast<int64_t>(plan.total), "scratch too small");
+    int32_t* rep = at<int32_t>(scratch, plan.off_rep);
+    float* cnt = at<float>(scratch, plan.off_cnt);
+    LabelScratch ls;
+    ls.own = at<int32_t>(scratch, plan.off_hown);
+    ls.hmin = at<int32_t>(scratch, plan.off_hmin);
+    ls.hcnt = at<int32_t>(scratch, plan.off_hcnt);
+    ls.skey = at<int32_t>(scratch, plan.off_skey);
+    ls.sidx = at<int32_t>(scratch, plan.off_sidx);
+    ls.iota = at<int32_t>(scratch, plan.off_iota);
+    ls.sort_tmp = at<void>(scratch, plan.off_sorttmp);
+    ls.sort_tmp_bytes = plan.sort_tmp_bytes;
+    int rc = 0;
+    if ((rc = launch_label_stats(labels, N, rep, cnt, ls, stream))) return rc;
+    if ((rc = launch_gscale(cnt, N, path, at<float>(scratch, plan.off_gscale), stream))) return rc;
+    return launch_class_ranges(ls.skey, rep, N, at<int32_t>(scratch, plan.off_cstart),
+                               at<int32_t>(scratch, plan.off_class_lo), stream);
+}
+
 // ---- the exported entry points: argument tuple -> CUDA-graph cache (graph_cache.h) -> the bodies above ---------------
 static GraphKey base_key(int tag, const void* const x[3], int dtype, const float* const inv_norm[3], int64_t N, int64_t d,
                          int64_t row0, int64_t n, float logit_scale, const float pair_weight[3], int path, int mode,
@@ -976,6 +1007,16 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
     return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
         return loss_forward_stats_impl(x, dtype, inv_norm, labels, N, d, row0, n, logit_scale, logit_scale_dev, pair_weight,
                                        path, mode, scratch, scratch_bytes, rowsum, colsum, posrow_out, pos, s);
+    });
+}
+
+int clibd_loss_label_stage(const int64_t* labels, int64_t N, int64_t n, int64_t d, int path, int mode, void* scratch,
+                           int64_t scratch_bytes, clibd_stream_t stream) {
+    NvtxRange nvtx_range("clibd_loss_label_stage");
+    GraphKey k;
+    k.add(6).add(labels).add(N).add(n).add(d).add(path).add(mode).add(scratch).add(scratch_bytes);
+    return run_graphed(k, graph_worthwhile(N, n), stream, [&](cudaStream_t s) {
+        return loss_label_stage_impl(labels, N, n, d, path, mode, scratch, scratch_bytes, s);
     });
 }
 

@@ -41,7 +41,7 @@ __global__ void shard_push_rows_kernel(const T* __restrict__ x0, const T* __rest
     const int64_t i = w - static_cast<int64_t>(m) * n;
     const T* xm = m == 0 ? x0 : (m == 1 ? x1 : x2);
     const int64_t grow = static_cast<int64_t>(rank) * n + i;
-    if (m == 0 && lane < world) peers.labels[lane][grow] = labels[i];
+    if (m == 0 && labels != nullptr && lane < world) peers.labels[lane][grow] = labels[i];
     if (xm == nullptr) return;
     const T* src = xm + i * d;
     float ss = 0.f;
@@ -138,7 +138,7 @@ int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t
                           int rank, int world, void* const peer_x[], float* const peer_inv[],
                           int64_t* const peer_labels[], clibd_stream_t stream) {
     NvtxRange nvtx_range("clibd_shard_push_rows");
-    CLIBD_REQUIRE(x_local && labels_local && peer_x && peer_inv && peer_labels, "null pointer");
+    CLIBD_REQUIRE(x_local && peer_x && peer_inv && peer_labels, "null pointer");  // labels_local may be null: rows only
     CLIBD_REQUIRE(n > 0 && d > 0 && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "bad shape or rank");
     CLIBD_REQUIRE(dtype == DT_F32 || dtype == DT_BF16 || dtype == DT_F16, "dtype must be 0, 1 or 2");
     const size_t esize = dtype == DT_F32 ? 4 : 2;
@@ -146,7 +146,7 @@ int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t
     bool vec = (d * esize) % 16 == 0;
     for (int q = 0; q < MAX_PEERS; ++q) {
         peers.labels[q] = q < world ? peer_labels[q] : nullptr;
-        if (q < world) CLIBD_REQUIRE(peer_labels[q] != nullptr, "null peer label buffer");
+        if (q < world && labels_local != nullptr) CLIBD_REQUIRE(peer_labels[q] != nullptr, "null peer label buffer");
         for (int m = 0; m < 3; ++m) {
             const bool on = q < world && x_local[m] != nullptr;
             peers.x[q * 3 + m] = on ? peer_x[q * 3 + m] : nullptr;

@@ -212,15 +212,37 @@ class _FusedClipLossFn(torch.autograd.Function):
                 # ---- exchanges are stores into peer-mapped memory; a barrier separates writers from readers
                 px = _peer.context(group, device, N, n, d, dtype, world, rank)
                 entry = px.acquire()
-                _lib.check(lib.clibd_shard_push_rows(
-                    _lib.ptr_array3([None if f is None else f.data_ptr() for f in local]), _DT[dtype], labels.data_ptr(),
-                    n, d, rank, world, entry.peer_x, entry.peer_inv, entry.peer_labels, stream))
-                px.barrier()
+                local_ptrs = _lib.ptr_array3([None if f is None else f.data_ptr() for f in local])
+                labels_arg = entry.labels_ptr
+                if os.environ.get("CLIBD_OVERLAP_PUSH", "1") != "0":
+                    # The labels (a few KB) go first; their statistics -- hash, class sort, ranges: ten small launches --
+                    # then run on this stream while the feature rows travel on a second one (NVLink-bound), each side with
+                    # its own barrier across the ranks.
+                    main = torch.cuda.current_stream(device)
+                    side = px.side_stream()
+                    side.wait_stream(main)  # the inputs are ready
+                    with torch.cuda.stream(side):
+                        _lib.check(lib.clibd_shard_push_rows(local_ptrs, _DT[dtype], None, n, d, rank, world, entry.peer_x,
+                                                             entry.peer_inv, entry.peer_labels,
+                                                             ctypes.c_void_p(side.cuda_stream)))
+                        px.barrier(channel=1)
+                    _lib.check(lib.clibd_shard_push_rows(_lib.ptr_array3([None, None, None]), _DT[dtype], labels.data_ptr(),
+                                                         n, d, rank, world, entry.peer_x, entry.peer_inv,
+                                                         entry.peer_labels, stream))
+                    px.barrier(channel=0)
+                    _lib.check(lib.clibd_loss_label_stage(entry.labels_ptr, N, n, d, path, mode, scratch.data_ptr(), nbytes,
+                                                          stream))
+                    main.wait_stream(side)
+                    labels_arg = None  # done
+                else:
+                    _lib.check(lib.clibd_shard_push_rows(local_ptrs, _DT[dtype], labels.data_ptr(), n, d, rank, world,
+                                                         entry.peer_x, entry.peer_inv, entry.peer_labels, stream))
+                    px.barrier()
                 gathered_ptrs = [None if f is None else entry.x_ptr[m] for m, f in enumerate(local)]
                 inv_ptrs = [None if f is None else entry.inv_ptr[m] for m, f in enumerate(local)]
                 xs, ivs = _lib.ptr_array3(gathered_ptrs), _lib.ptr_array3(inv_ptrs)
                 st = entry.stats_ptr
-                _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, entry.labels_ptr, N, d, row0, n, scale_value,
+                _lib.check(lib.clibd_loss_forward_stats(xs, _DT[dtype], ivs, labels_arg, N, d, row0, n, scale_value,
                                                         scale_ptr, w, path, mode, scratch.data_ptr(), nbytes, st,
                                                         st + 12 * N, st + 24 * N, entry.pos_local_ptr, stream))
                 _lib.check(lib.clibd_shard_push_stats(st, entry.pos_local_ptr, N, row0, n, rank, world, entry.peer_stats,

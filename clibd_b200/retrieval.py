@@ -113,7 +113,7 @@ def merge_topk(sims64_parts: torch.Tensor, idx_parts: torch.Tensor):
 
 _PIPELINE_MIN_KEYS = 1 << 17   # host-resident key sets at least this large are copied and searched block-wise
 _PIPELINE_BLOCKS = 4           # measured (tools/knn_blocks.py, 100k x 1M): 2 -> 157 ms, 4 -> 155, 8 -> 161, 16 -> 194
-_PIPELINE_BLOCK_KEYS = 1 << 18  # ... but no block below ~256k keys: every block pays its own re-rank pass
+_PIPELINE_BLOCK_KEYS = 1 << 16  # ... but no block below ~64k keys: every block pays its own re-rank pass (~2 ms)
 
 
 def _pipeline_blocks(nkeys: int) -> int:

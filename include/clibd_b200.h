@@ -80,6 +80,7 @@ int64_t clibd_loss_scratch_bytes(int64_t n_global, int64_t n_local, int64_t d, i
  * call, of clibd_loss_forward_finish and of clibd_loss_backward reads it from there -- no host read per step.
  * The scale must be a positive finite number (host value: error otherwise; device value: NaN loss); it is NOT limited
  * from above -- the reference never clamps its learnable scale -- the kernels choose their softmax shift from it.
+ * labels == NULL: clibd_loss_label_stage has already run on this scratch.
  * mode 1 (exchange) additionally writes posrow[p*n_global + i] = xhat_a[i] . sum_{j: label_j = label_i} xhat_b[j] for the
  * LOCAL rows i of every weighted pair p = (a, b) (disjoint support across ranks: all-reduce / exchange it like rowsum;
  * the backward needs it for all rows); posrow may be NULL in mode 0. */
@@ -88,6 +89,11 @@ int clibd_loss_forward_stats(const void* const x[3], int dtype, const float* con
                              float logit_scale, const float* logit_scale_dev, const float pair_weight[3] /* host */,
                              int path, int mode, void* scratch, int64_t scratch_bytes, float* rowsum, float* colsum,
                              float* posrow, double* pos, clibd_stream_t stream);
+
+/* The label statistics of clibd_loss_forward_stats alone (class representatives and sizes, class sort, positive
+ * ranges): call it as soon as the gathered labels are there, then clibd_loss_forward_stats with labels == NULL. */
+int clibd_loss_label_stage(const int64_t* labels, int64_t n_global, int64_t n_local, int64_t d, int path, int mode,
+                           void* scratch, int64_t scratch_bytes, clibd_stream_t stream);
 
 /* Loss value from complete statistics (rowsum/colsum/pos now hold GLOBAL sums for all
  * n_global rows/columns); also prepares the backward coefficients inside scratch.  The scale used is the one
@@ -155,7 +161,9 @@ int clibd_loss_backward_finish(const void* const x[3], int dtype, const float* c
  * clibd_shard_push_rows: the all-gather.  Copies this rank's n_local rows of every present modality (raw, `dtype`),
  * their inverse norms (computed here, as clibd_row_inv_norm) and its labels into rows [rank * n_local, (rank+1) *
  * n_local) of EVERY rank's gathered buffers: peer_x[q*3+m] = [n_global, d] in `dtype`, peer_inv[q*3+m] = [n_global]
- * float32, peer_labels[q] = [n_global] int64. */
+ * float32, peer_labels[q] = [n_global] int64.  labels_local == NULL: feature rows and inverse norms only; every
+ * x_local[m] == NULL: labels only (a sharded step sends the labels ahead so that the label statistics run next to the
+ * push of the feature rows). */
 int clibd_shard_push_rows(const void* const x_local[3], int dtype, const int64_t* labels_local, int64_t n_local,
                           int64_t d, int rank, int world, void* const peer_x[] /* host */,
                           float* const peer_inv[] /* host */, int64_t* const peer_labels[] /* host */,

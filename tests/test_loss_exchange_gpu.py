@@ -27,7 +27,8 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6, 1 / 6), grad_outs=None):
+def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6, 1 / 6), grad_outs=None,
+                  labels_first=False):
     """feats: list of 3 [N, d] CUDA tensors (or None); returns loss per rank, grads [3][N, d] float32, dscale."""
     from clibd_b200 import _lib
     from clibd_b200.loss import _DT, _column_slots
@@ -61,15 +62,21 @@ def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6
     def P(t):
         return None if t is None else t.data_ptr()
 
-    # ---- all-gather by pushes
+    # ---- all-gather by pushes (labels_first: the labels travel in their own push, as the overlapped step sends them)
     for r in R:
         loc = [None if f is None else f[r * n:(r + 1) * n].contiguous() for f in feats]
         lab = labels[r * n:(r + 1) * n].contiguous()
-        _lib.check(lib.clibd_shard_push_rows(
-            _lib.ptr_array3([P(t) for t in loc]), dt, lab.data_ptr(), n, d, r, world,
-            _lib.ptr_array([P(gx[q][m]) for q in R for m in range(3)]),
-            _lib.ptr_array([P(ginv[q][m]) for q in R for m in range(3)]),
-            _lib.ptr_array([glab[q].data_ptr() for q in R]), stream))
+        tables = (_lib.ptr_array([P(gx[q][m]) for q in R for m in range(3)]),
+                  _lib.ptr_array([P(ginv[q][m]) for q in R for m in range(3)]),
+                  _lib.ptr_array([glab[q].data_ptr() for q in R]))
+        if labels_first:
+            _lib.check(lib.clibd_shard_push_rows(_lib.ptr_array3([None, None, None]), dt, lab.data_ptr(), n, d, r, world,
+                                                 *tables, stream))
+            _lib.check(lib.clibd_shard_push_rows(_lib.ptr_array3([P(t) for t in loc]), dt, None, n, d, r, world, *tables,
+                                                 stream))
+        else:
+            _lib.check(lib.clibd_shard_push_rows(_lib.ptr_array3([P(t) for t in loc]), dt, lab.data_ptr(), n, d, r, world,
+                                                 *tables, stream))
     torch.cuda.synchronize()
     for q in R:  # every rank now holds the whole batch, bit-identical
         assert torch.equal(glab[q], labels)
@@ -81,8 +88,12 @@ def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6
     scale_dev = torch.tensor([scale], device=dev)
     for r in R:
         st = stats[r].data_ptr()
+        if labels_first:  # label statistics in their own call, then forward_stats with labels == NULL
+            _lib.check(lib.clibd_loss_label_stage(glab[r].data_ptr(), N, n, d, path, mode, scratch[r].data_ptr(), nbytes,
+                                                  stream))
         _lib.check(lib.clibd_loss_forward_stats(
-            _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]), glab[r].data_ptr(), N, d,
+            _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]),
+            None if labels_first else glab[r].data_ptr(), N, d,
             r * n, n, 0.0, scale_dev.data_ptr(), w, path, mode, scratch[r].data_ptr(), nbytes, st, st + 12 * N,
             st + 24 * N, pos_local[r].data_ptr(), stream))
     for r in R:
@@ -171,7 +182,7 @@ def test_simulated_ranks_match_oracle(form, N, d, nmod, world, operands, labels_
     grad_outs = [1.0 + 0.5 * r for r in range(world)]  # a different upstream gradient on every rank: the SUM scales dx
     gsum = sum(grad_outs)
     losses, grads, ds = _sharded_step([None if f is None else f.to(dev) for f in feats], labels.to(dev), scale, world,
-                                      path, form, weights, grad_outs)
+                                      path, form, weights, grad_outs, labels_first=(form == "peer"))
     for l in losses:
         assert abs(l - ref["loss"]) <= 1e-3 * abs(ref["loss"])
         assert l == losses[0]  # bit-identical on every rank
