@@ -214,10 +214,13 @@ class _FusedClipLossFn(torch.autograd.Function):
                 entry = px.acquire()
                 local_ptrs = _lib.ptr_array3([None if f is None else f.data_ptr() for f in local])
                 labels_arg = entry.labels_ptr
-                if os.environ.get("CLIBD_OVERLAP_PUSH", "1") != "0":
-                    # The labels (a few KB) go first; their statistics -- hash, class sort, ranges: ten small launches --
-                    # then run on this stream while the feature rows travel on a second one (NVLink-bound), each side with
-                    # its own barrier across the ranks.
+                if os.environ.get("CLIBD_OVERLAP_PUSH", "0") != "0":
+                    # Optional (off by default): the labels (a few KB) go first; their statistics -- hash, class sort,
+                    # ranges: ten small launches -- then run on this stream while the feature rows travel on a second one
+                    # (NVLink-bound), each side with its own barrier across the ranks.  Measured at 8 GPUs, N = 32768:
+                    # 2.694 ms per step with it, 2.681 ms without (profiles/r2n_phase_timing_n8.log) -- the second
+                    # barrier and the stream joins cost what the overlap saves, and small batches lose (N = 4096:
+                    # 0.74 vs 0.64 ms), so the plain sequence below is the default.
                     main = torch.cuda.current_stream(device)
                     side = px.side_stream()
                     side.wait_stream(main)  # the inputs are ready
