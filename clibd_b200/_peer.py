@@ -158,13 +158,23 @@ class EntryHolder:
             pass
 
 
+_MAX_CONTEXTS = 4  # distinct (batch, dim, dtype) configurations kept mapped; a training loop uses one or two
+
+
 def context(group, device, N, n, d, dtype, world, rank) -> PeerContext:
     group = group if group is not None else dist.group.WORLD
     key = (group.group_name, device.index, N, n, d, dtype, world, rank)
-    px = _contexts.get(key)
+    px = _contexts.pop(key, None)
     if px is None:
+        # Least recently used configurations whose buffers no forward still holds are dropped first.  Every rank sees
+        # the same sequence of shapes (SPMD), so every rank drops and allocates at the same call.
+        for old_key in list(_contexts):
+            if len(_contexts) < _MAX_CONTEXTS:
+                break
+            if not any(e.busy for e in _contexts[old_key].entries):
+                del _contexts[old_key]
         px = PeerContext(group, device, N, n, d, dtype, world, rank)
-        _contexts[key] = px
+    _contexts[key] = px  # (re)inserted last: dict order = recency
     return px
 
 

@@ -311,9 +311,10 @@ class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t* __restrict__ sk
 // MO_ROWS x 64 tile: xh[row][col] = cvt(x * inv) (zero for col >= d), xhT[col][row] (zero for row >= N); 16-byte
 // global accesses on both outputs (and on the input when rows are 16-byte aligned).  With perm the tile walks the
 // rows in permuted order: position k holds input row perm[k]; xh stays in input order, xhS / xhT follow perm.
-// 128 rows per tile: a column of the transposed copy then receives 256 contiguous bytes per tile (64-row tiles wrote
-// 128-byte pieces 2 N bytes apart and reached 28 % of the DRAM rate, ncu).
-constexpr int MO_ROWS = 128;
+// (64 rows per tile: a column of the transposed copy receives 128 contiguous bytes per tile.  128-row tiles -- 256-byte
+//  pieces -- were tried and were slower, 61 against 41 us per 32768 x 768 modality: the transposing shared-memory reads
+//  become 16-way bank conflicts.)
+constexpr int MO_ROWS = 64;
 template <typename T, bool VEC>
 __global__ void make_operands_kernel(const T* __restrict__ x, const float* __restrict__ inv, int64_t N, int64_t d,
                                      int64_t dpad, int64_t npad, int fmt_bf16, uint16_t* __restrict__ xh,
