@@ -311,10 +311,13 @@ class_sums_jobs_kernel(JobList<ClassSumJob> jobs, const int32_t* __restrict__ sk
 // MO_ROWS x 64 tile: xh[row][col] = cvt(x * inv) (zero for col >= d), xhT[col][row] (zero for row >= N); 16-byte
 // global accesses on both outputs (and on the input when rows are 16-byte aligned).  With perm the tile walks the
 // rows in permuted order: position k holds input row perm[k]; xh stays in input order, xhS / xhT follow perm.
-// (64 rows per tile: a column of the transposed copy receives 128 contiguous bytes per tile.  128-row tiles -- 256-byte
-//  pieces -- were tried and were slower, 61 against 41 us per 32768 x 768 modality: the transposing shared-memory reads
-//  become 16-way bank conflicts.)
-constexpr int MO_ROWS = 64;
+// (64 rows per tile: a column of the transposed copy receives 128 contiguous bytes per tile.  The tile is chunk-swizzled
+//  so that the transposing shared-memory reads are conflict-free: 41 -> 28 us per 32768 x 768 modality.  128-row tiles
+//  (256-byte pieces, -DCLIBD_MO_ROWS=128) measured the same with the swizzle and slower without it.)
+#ifndef CLIBD_MO_ROWS
+#define CLIBD_MO_ROWS 64
+#endif
+constexpr int MO_ROWS = CLIBD_MO_ROWS;
 template <typename T, bool VEC>
 __global__ void make_operands_kernel(const T* __restrict__ x, const float* __restrict__ inv, int64_t N, int64_t d,
                                      int64_t dpad, int64_t npad, int fmt_bf16, uint16_t* __restrict__ xh,
@@ -344,7 +347,9 @@ __global__ void make_operands_kernel(const T* __restrict__ x, const float* __res
         uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = pack2_operand16(v[2 * k], v[2 * k + 1], fmt_bf16);
-        *reinterpret_cast<uint4*>(&tile[rr][ch * 8]) = pk;
+        // 16-byte chunk ch of row rr sits at chunk position ch ^ (rr / 8 mod 8): the transposing reads below (8 row groups
+        // per column) then hit 8 different banks instead of one
+        *reinterpret_cast<uint4*>(&tile[rr][(ch ^ ((rr >> 3) & 7)) * 8]) = pk;
         if (row < N && col < dpad) {
             if (xh) *reinterpret_cast<uint4*>(xh + src * dpad + col) = pk;
             if (xhS) *reinterpret_cast<uint4*>(xhS + row * dpad + col) = pk;
@@ -359,7 +364,7 @@ __global__ void make_operands_kernel(const T* __restrict__ x, const float* __res
                 uint4 pk;
                 uint16_t* h = reinterpret_cast<uint16_t*>(&pk);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) h[k] = tile[rch * 8 + k][cc];
+                for (int k = 0; k < 8; ++k) h[k] = tile[rch * 8 + k][((((cc >> 3) ^ (rch & 7)) << 3) | (cc & 7))];
                 *reinterpret_cast<uint4*>(xhT + col * npad + row) = pk;
             }
         }
