@@ -246,7 +246,8 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         p.strip_rows = rows < all ? rows : all;
         p.gt_ld = p.strip_rows;  // Gs[n local rows][strip columns]
         p.off_gt = take(2 * static_cast<size_t>(n) * p.gt_ld);
-        p.off_gt2 = take(2 * static_cast<size_t>(n) * p.gt_ld);  // (image, text) and (dna, text) feed one gradient GEMM
+        // sharded step: (image, text) and (dna, text) feed ONE gradient GEMM, each from its own strip
+        p.off_gt2 = p.exchange ? take(2 * static_cast<size_t>(n) * p.gt_ld) : p.off_gt;
         p.npad_loc = round_up(n, 8);
         for (int m = 0; m < 3; ++m) {
             p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad_loc);

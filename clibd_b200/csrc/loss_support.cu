@@ -628,11 +628,22 @@ __global__ void normalize_bwd_kernel(NormBwdList list) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) g[k] += t[k];
             }
-            for (int s = 0; s < a.extra_slots; ++s) {
-                float t[8];
-                load8(a.extra + (static_cast<int64_t>(s) * a.n + i) * a.d + c, t);
+            // the received slots (one per source rank): four loads in flight, added in slot order
+            for (int s0 = 0; s0 < a.extra_slots; s0 += 4) {
+                float t[4][8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) g[k] += t[k];
+                for (int u = 0; u < 4; ++u) {
+                    if (s0 + u < a.extra_slots) {
+                        load8(a.extra + (static_cast<int64_t>(s0 + u) * a.n + i) * a.d + c, t[u]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) t[u][k] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[k] += t[u][k];
             }
             float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll

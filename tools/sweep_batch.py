@@ -58,7 +58,7 @@ def main():
                 steps = 10 if N <= 32768 else (4 if N <= 65536 else 2)
                 torch.cuda.reset_peak_memory_stats(dev)
                 base = torch.cuda.memory_allocated(dev)
-                for _ in range(2 if N <= 65536 else 1):
+                for _ in range(2):  # two warm-up steps: the first one of a new shape allocates (and maps) its buffers
                     loss = step()
                 if world > 1:
                     dist.barrier()
