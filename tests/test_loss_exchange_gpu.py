@@ -232,3 +232,31 @@ def test_side_stream_overlap_is_bit_identical(monkeypatch):
         assert got[0] == ref[0] and got[2] == ref[2]
         for a, b in zip(got[1], ref[1]):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("bind_to,no_it,weights", [
+    ("image", False, (0.25, 0.25, 0.0)),   # bind_to="image": (image,dna) and (image,text); text's only column pair is pair 1
+    (None, True, (0.25, 0.0, 0.25)),       # no_image_text_loss: (image,dna) and (dna,text); text's column pair is pair 2
+    ("text", False, (0.0, 0.25, 0.25)),    # bind_to="text": both weighted pairs share the column modality -> one merged GEMM
+])
+def test_simulated_ranks_pair_filters(bind_to, no_it, weights):
+    """The reference's pair filters (loss_func.py:166-184) change which pairs exist, hence which slot array receives a
+    column modality's partial gradients and whether two pairs are merged into one gradient GEMM."""
+    from clibd_b200 import _lib
+    from clibd_b200.loss import pair_weights
+    assert tuple(pair_weights([True, True, True], bind_to, no_it)[0]) == pytest.approx(weights)
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(8)
+    N, d, world = 512, 768, 2
+    feats = [torch.randn(N, d, generator=gen).bfloat16() for _ in range(3)]
+    labels = torch.randint(0, N // 8, (N,), generator=gen)
+    scale = 1 / 0.07
+    ref = lo.contrastive_loss([f.float().numpy() for f in feats], labels.numpy(), scale, bind_to=bind_to,
+                              no_image_text_loss=no_it)
+    for form in ("peer", "reduce_scatter"):
+        losses, grads, ds = _sharded_step([f.to(dev) for f in feats], labels.to(dev), scale, world, _lib.PATH_TC_F16, form,
+                                          weights)
+        assert abs(losses[0] - ref["loss"]) <= 1e-3 * abs(ref["loss"])
+        for i in range(3):
+            assert _rel(grads[i], world * ref["grads"][i]) < 1e-3 + 2 ** -8, (form, i)
+        assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
