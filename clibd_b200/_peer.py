@@ -38,8 +38,23 @@ _contexts = {}
 _probe = {}
 
 
+_disabled_reason = None
+
+
 def available() -> bool:
-    return _symm is not None and torch.cuda.is_available()
+    return _symm is not None and torch.cuda.is_available() and _disabled_reason is None
+
+
+def disable(reason: str):
+    """Called when mapping the ranks' buffers into each other failed (an environment without peer access / fd passing):
+    the sharded step then uses its NCCL form for the rest of the process.  The failure is a property of the box, so
+    every rank takes the same branch."""
+    global _disabled_reason
+    if _disabled_reason is None:
+        import warnings
+        warnings.warn("clibd_b200: peer-mapped exchange unavailable (" + reason + "); using the NCCL form of the sharded "
+                      "loss step")
+        _disabled_reason = reason
 
 
 def _align(v, a=256):

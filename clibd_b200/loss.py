@@ -183,8 +183,17 @@ class _FusedClipLossFn(torch.autograd.Function):
         n, d = ref.shape
         stream = _stream_ptr(device)
         shard = _shard_mode(path, d, group, device) if world > 1 else "single"
+        px = entry = None
+        if shard == "peer":
+            try:
+                px = _peer.context(group, device, n * world, n, d, ref.dtype, world, rank)
+                entry = px.acquire()
+            except Exception as ex:  # noqa: BLE001  (no peer access / no way to pass the handles on this box)
+                if os.environ.get("CLIBD_SHARD_MODE", "") == "peer":
+                    raise
+                _peer.disable(repr(ex))
+                shard, px, entry = "nccl", None, None
         mode = _lib.MODE_EXCHANGE if shard in ("peer", "nccl") else _lib.MODE_LOCAL
-        entry = None
         with _device_ctx(device):
             local = [None if f is None else f.detach().contiguous() for f in feats]
             labels = labels.detach().to(device=device, dtype=torch.int64).contiguous()
@@ -210,8 +219,6 @@ class _FusedClipLossFn(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=device)
             if shard == "peer":
                 # ---- exchanges are stores into peer-mapped memory; a barrier separates writers from readers
-                px = _peer.context(group, device, N, n, d, dtype, world, rank)
-                entry = px.acquire()
                 local_ptrs = _lib.ptr_array3([None if f is None else f.data_ptr() for f in local])
                 labels_arg = entry.labels_ptr
                 if os.environ.get("CLIBD_OVERLAP_PUSH", "0") != "0":
