@@ -154,6 +154,40 @@ class PeerContext:
         return self._parity
 
 
+class GatherBuffers:
+    """Receive buffer of the stand-alone differentiable all-gather (loss.gather_features): [N, d] rows + [N] inverse
+    norms (clibd_shard_push_rows always writes them).  One copy is enough: the caller reads the gathered rows between
+    two barriers, so no rank can push the next call's rows before every rank has finished reading this call's."""
+
+    def __init__(self, group, device, N, d, dtype, world, rank):
+        esize = torch.empty((), dtype=dtype).element_size()
+        x_bytes = _align(N * d * esize)
+        self.region = _Region(x_bytes + 4 * N, device, group)
+        base = self.region.ptrs
+        self.peer_x = _lib.ptr_array([base[q] if m == 0 else None for q in range(world) for m in range(3)])
+        self.peer_inv = _lib.ptr_array([base[q] + x_bytes if m == 0 else None for q in range(world) for m in range(3)])
+        self.peer_labels = _lib.ptr_array([None] * world)
+        self.rows = self.region.tensor[:N * d * esize].view(dtype).view(N, d)
+
+    def barrier(self):
+        self.region.handle.barrier()
+
+
+_gather_buffers = {}
+
+
+def gather_buffers(group, device, N, d, dtype, world, rank) -> GatherBuffers:
+    group = group if group is not None else dist.group.WORLD
+    key = (group.group_name, device.index, N, d, dtype, world, rank)
+    gb = _gather_buffers.pop(key, None)
+    if gb is None:
+        while len(_gather_buffers) >= _MAX_CONTEXTS:
+            del _gather_buffers[next(iter(_gather_buffers))]  # least recently used (same sequence on every rank)
+        gb = GatherBuffers(group, device, N, d, dtype, world, rank)
+    _gather_buffers[key] = gb
+    return gb
+
+
 class EntryHolder:
     """Releases a pool entry when the backward has run, or when autograd drops a forward that will have none."""
 
@@ -196,3 +230,4 @@ def context(group, device, N, n, d, dtype, world, rank) -> PeerContext:
 def reset():
     """Drop every cached context (tests; frees the symmetric allocations)."""
     _contexts.clear()
+    _gather_buffers.clear()

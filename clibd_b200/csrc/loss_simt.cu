@@ -13,8 +13,11 @@ namespace clibd {
 namespace {
 
 constexpr int T64 = SIMT_T;
-constexpr int KT = 16;
+constexpr int KT = 32;
 
+// Both kernels are latency-bound at the batches this path serves (N <= 1024; BASELINE config 1 is N = 256: 16 forward
+// tiles): every thread keeps the NEXT K chunk of both operands in registers while the current one is consumed from
+// shared memory, so the global-load latency of a chunk hides behind the FMAs of the one before.
 template <typename T>
 __global__ void __launch_bounds__(256)
 simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float* __restrict__ inv_a,
@@ -26,7 +29,7 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
     __shared__ float Bs[KT][T64 + 1];
     __shared__ float red[T64][17];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 15, ty = tid >> 4;  // rows ty * 4 + i, columns tx + 16 * j (conflict-free Bs reads)
     const int64_t ct = blockIdx.x, rt = blockIdx.y;
     const int64_t lrow0 = rt * T64;          // local row base
     const int64_t col0 = ct * T64;           // global column base
@@ -36,27 +39,45 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    // loader: element q of this thread = (tile row lr8 + 8 q, k = lane); a warp reads 32 consecutive k of one row
+    const int lk = tid & 31, lr8 = tid >> 5;
+    const T* pa_row[8];
+    const T* pb_row[8];
+    float ia[8], ib[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int64_t lr = lrow0 + lr8 + 8 * q, gc = col0 + lr8 + 8 * q;
+        const bool va = lr < n, vb = gc < N;
+        pa_row[q] = va ? xa + (row0 + lr) * d : nullptr;
+        pb_row[q] = vb ? xb + gc * d : nullptr;
+        ia[q] = va ? inv_a[row0 + lr] : 0.f;
+        ib[q] = vb ? inv_b[gc] : 0.f;
+    }
+    float pa[8], pb[8];
+    auto fetch = [&](int64_t k0) {
+        const int64_t gk = k0 + lk;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            pa[q] = (pa_row[q] != nullptr && gk < d) ? load_as_float(pa_row[q], gk) * ia[q] : 0.f;
+            pb[q] = (pb_row[q] != nullptr && gk < d) ? load_as_float(pb_row[q], gk) * ib[q] : 0.f;
+        }
+    };
+    fetch(0);
     for (int64_t k0 = 0; k0 < d; k0 += KT) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int idx = tid + 256 * q;
-            const int r = idx >> 4, k = idx & 15;
-            const int64_t lr = lrow0 + r, gk = k0 + k;
-            float va = 0.f, vb = 0.f;
-            if (lr < n && gk < d) va = load_as_float(xa + (row0 + lr) * d, gk) * inv_a[row0 + lr];
-            const int64_t gc = col0 + r;
-            if (gc < N && gk < d) vb = load_as_float(xb + gc * d, gk) * inv_b[gc];
-            As[k][r] = va;
-            Bs[k][r] = vb;
+        for (int q = 0; q < 8; ++q) {
+            As[lk][lr8 + 8 * q] = pa[q];
+            Bs[lk][lr8 + 8 * q] = pb[q];
         }
         __syncthreads();
+        if (k0 + KT < d) fetch(k0 + KT);
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             float a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -64,15 +85,16 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
         }
         __syncthreads();
     }
-    // e = exp(S - s); |S| <= s for unit vectors so the fixed shift is safe
+    // e = exp(S - shift); |S| <= s for unit vectors so the fixed shift is safe
     float rsum[4] = {0.f, 0.f, 0.f, 0.f}, csum[4] = {0.f, 0.f, 0.f, 0.f};
+    const float shift = softmax_shift(scale);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const bool valid = (lrow0 + ty * 4 + i < n) && (col0 + tx * 4 + j < N) &&
-                               !(self_mask && row0 + lrow0 + ty * 4 + i == col0 + tx * 4 + j);
-            const float e = valid ? expf(fmaf(scale, acc[i][j], -softmax_shift(scale))) : 0.f;
+            const bool valid = (lrow0 + ty * 4 + i < n) && (col0 + tx + 16 * j < N) &&
+                               !(self_mask && row0 + lrow0 + ty * 4 + i == col0 + tx + 16 * j);
+            const float e = valid ? expf(fmaf(scale, acc[i][j], -shift)) : 0.f;
             rsum[i] += e;
             csum[j] += e;
         }
@@ -88,7 +110,7 @@ simt_fwd_kernel(const T* __restrict__ xa, const T* __restrict__ xb, const float*
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[tx * 4 + j][ty] = csum[j];
+    for (int j = 0; j < 4; ++j) red[tx + 16 * j][ty] = csum[j];
     __syncthreads();
     if (tid < T64) {
         float t = 0.f;
@@ -127,23 +149,47 @@ simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* _
     for (int r = 0; r < BR; ++r)
 #pragma unroll
         for (int q = 0; q < DQ; ++q) acc[r][q] = 0.f;
+    const float shift = softmax_shift(scale);
+
+    // loader of the S operands: element q of this thread = (tile row lr8 + 8 q, k = lane)
+    const int lk = tid & 31, lr8 = tid >> 5;
+    const T* px_row[4];
+    float ix[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t lr = lr0 + lr8 + 8 * q;
+        px_row[q] = lr < n ? x + (row0 + lr) * d : nullptr;
+        ix[q] = lr < n ? inv_x[row0 + lr] : 0.f;
+    }
 
     for (int64_t j0 = j_begin; j0 < j_end; j0 += BJ) {
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        const T* py_row[4];
+        float iy[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t gj = j0 + lr8 + 8 * q;
+            py_row[q] = gj < N ? y + gj * d : nullptr;
+            iy[q] = gj < N ? inv_y[gj] : 0.f;
+        }
+        float pxv[4], pyv[4];
+        auto fetch = [&](int64_t k0) {  // the next K chunk waits in registers while the current one is consumed
+            const int64_t gk = k0 + lk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                pxv[q] = (px_row[q] != nullptr && gk < d) ? load_as_float(px_row[q], gk) * ix[q] : 0.f;
+                pyv[q] = (py_row[q] != nullptr && gk < d) ? load_as_float(py_row[q], gk) * iy[q] : 0.f;
+            }
+        };
+        fetch(0);
         for (int64_t k0 = 0; k0 < d; k0 += BJ) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int idx = tid + 256 * q;
-                const int r = idx >> 5, k = idx & 31;
-                const int64_t gk = k0 + k;
-                const int64_t lr = lr0 + r, gj = j0 + r;
-                float vx = 0.f, vy = 0.f;
-                if (lr < n && gk < d) vx = load_as_float(x + (row0 + lr) * d, gk) * inv_x[row0 + lr];
-                if (gj < N && gk < d) vy = load_as_float(y + gj * d, gk) * inv_y[gj];
-                Xs[r][k] = vx;
-                Ys[r][k] = vy;
+                Xs[lr8 + 8 * q][lk] = pxv[q];
+                Ys[lr8 + 8 * q][lk] = pyv[q];
             }
             __syncthreads();
+            if (k0 + BJ < d) fetch(k0 + BJ);
 #pragma unroll
             for (int k = 0; k < BJ; ++k) {
                 const float xv = Xs[srow][k];
@@ -160,26 +206,34 @@ simt_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* _
                 const int64_t gj = j0 + scol + c;
                 float g = 0.f;
                 if (lr < n && gj < N && !(self_mask && row0 + lr == gj))
-                    g = expf(fmaf(scale, s4[c], -softmax_shift(scale))) * (rc + colcoef[gj]);
+                    g = expf(fmaf(scale, s4[c], -shift)) * (rc + colcoef[gj]);
                 Gs[srow][scol + c] = g;
             }
         }
         __syncthreads();
+        // dXhat rows += G~ Yhat: four column rows of Yhat in flight per thread (G~ of a column that does not exist is 0)
         const int jmax = static_cast<int>(min(static_cast<int64_t>(BJ), N - j0));
-        for (int jj = 0; jj < jmax; ++jj) {
-            const int64_t gj = j0 + jj;
-            const float iv = inv_y[gj];
-            float yv[DQ];
+        for (int jj = 0; jj < jmax; jj += 4) {
+            float yv[4][DQ];
 #pragma unroll
-            for (int q = 0; q < DQ; ++q) {
-                const int64_t c = dbase + tid + 256 * q;
-                yv[q] = (c < d) ? load_as_float(y + gj * d, c) * iv : 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const int64_t gj = j0 + jj + u;
+                const bool jv = jj + u < jmax;
+                const float iv = jv ? inv_y[gj] : 0.f;
+#pragma unroll
+                for (int q = 0; q < DQ; ++q) {
+                    const int64_t c = dbase + tid + 256 * q;
+                    yv[u][q] = (jv && c < d) ? load_as_float(y + gj * d, c) * iv : 0.f;
+                }
             }
 #pragma unroll
-            for (int r = 0; r < BR; ++r) {
-                const float g = Gs[r][jj];
+            for (int u = 0; u < 4; ++u) {
 #pragma unroll
-                for (int q = 0; q < DQ; ++q) acc[r][q] = fmaf(g, yv[q], acc[r][q]);
+                for (int r = 0; r < BR; ++r) {
+                    const float g = Gs[r][jj + u];
+#pragma unroll
+                    for (int q = 0; q < DQ; ++q) acc[r][q] = fmaf(g, yv[u][q], acc[r][q]);
+                }
             }
         }
         __syncthreads();

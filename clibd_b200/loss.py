@@ -458,11 +458,64 @@ class ContrastiveLoss(nn.Module):
                            self.tensor_core_operands, None, 1, 0, True)
 
 
+class _PeerAllGatherFn(torch.autograd.Function):
+    """Differentiable all-gather of [n, d] rows as stores into peer-mapped memory (clibd_shard_push_rows); backward =
+    reduce-scatter(SUM) of the gathered gradient, like torch.distributed.nn.all_gather's (loss_func.py:97)."""
+
+    @staticmethod
+    def forward(ctx, features, group, world, rank):
+        lib = _lib.load()
+        device, dtype = features.device, features.dtype
+        n, d = features.shape
+        gb = _peer.gather_buffers(group, device, n * world, d, dtype, world, rank)
+        with _device_ctx(device):
+            x = features.detach().contiguous()
+            _lib.check(lib.clibd_shard_push_rows(_lib.ptr_array3([x.data_ptr(), None, None]), _DT[dtype], None, n, d, rank,
+                                                 world, gb.peer_x, gb.peer_inv, gb.peer_labels, _stream_ptr(device)))
+            gb.barrier()   # every rank's rows have landed in every buffer
+            out = gb.rows.clone()
+            gb.barrier()   # every rank has read its buffer: the next call may overwrite it
+        ctx.meta = (n, rank, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        n, rank, group = ctx.meta
+        return _reduce_scatter_rows(grad.contiguous(), n, rank, group), None, None, None
+
+
+def _peer_gather_ok(features, world):
+    if world <= 1 or not isinstance(features, torch.Tensor) or not features.is_cuda or features.dim() != 2:
+        return False
+    if features.dtype not in _DT or features.shape[0] == 0 or os.environ.get("CLIBD_SHARD_MODE", "") in ("nccl", "local"):
+        return False
+    try:
+        return _peer.available() and dist.is_initialized() and dist.get_backend() == "nccl" \
+            and dist.get_world_size() == world
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def gather_features(features, local_loss=False, gather_with_grad=False, rank=0, world_size=1, use_horovod=False):
-    """loss_func.py:73-106 (public helper of the reference module; the fused ClipLoss does not call it)."""
+    """loss_func.py:73-106 (public helper of the reference module; the fused ClipLoss gathers inside its own step).
+    CUDA [n, d] features under NCCL travel as stores into peer-mapped memory over NVLink (this library's push kernel)
+    where the ranks can map each other's buffers; otherwise the reference's collectives are used."""
     assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
     if use_horovod:
         raise NotImplementedError("horovod is not supported (no shipped reference config uses it)")
+    if _peer_gather_ok(features, world_size):
+        try:
+            if gather_with_grad:
+                return _PeerAllGatherFn.apply(features, None, world_size, rank)
+            n = features.shape[0]
+            all_features = _PeerAllGatherFn.apply(features.detach(), None, world_size, rank)
+            if not local_loss:  # grads for the local rows when the gathered features carry none
+                all_features = torch.cat([all_features[:rank * n], features, all_features[(rank + 1) * n:]], dim=0)
+            return all_features
+        except RuntimeError as ex:  # mapping the buffers failed on this box: the NCCL form below, from now on
+            if os.environ.get("CLIBD_SHARD_MODE", "") == "peer":
+                raise
+            _peer.disable(repr(ex))
     if gather_with_grad:
         return torch.cat(torch.distributed.nn.all_gather(features), dim=0)
     gathered = [torch.zeros_like(features) for _ in range(world_size)]

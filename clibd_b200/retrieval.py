@@ -112,12 +112,26 @@ def merge_topk(sims64_parts: torch.Tensor, idx_parts: torch.Tensor):
 
 
 _PIPELINE_MIN_KEYS = 1 << 17   # host-resident key sets at least this large are copied and searched block-wise
-_PIPELINE_BLOCKS = 4           # measured (tools/knn_blocks.py, 100k x 1M): 2 -> 157 ms, 4 -> 155, 8 -> 161, 16 -> 194
-_PIPELINE_BLOCK_KEYS = 1 << 16  # ... but no block below ~64k keys: every block pays its own re-rank pass (~2 ms)
+_PIPELINE_FIRST_KEYS = 1 << 15  # first block: its copy (100 MB at d = 768, ~2 ms) is the only one nothing hides
+_PIPELINE_GROWTH = 2           # a block's copy runs next to the previous block's screen, which takes ~2x as long per key
+_PIPELINE_BLOCKS = 6           # every block pays its own re-rank pass (~2.4 ms at 100k queries): keep them few
 
 
-def _pipeline_blocks(nkeys: int) -> int:
-    return max(1, min(_PIPELINE_BLOCKS, (nkeys + _PIPELINE_BLOCK_KEYS - 1) // _PIPELINE_BLOCK_KEYS))
+def _pipeline_bounds(lo: int, hi: int, blocks=None):
+    """Block boundaries of the pipelined host-key search.  Default: geometrically growing blocks -- a small first block
+    (its copy is exposed), every later one as large as the copy the previous block's compute can hide, the last takes
+    the rest.  Equal blocks (tools/knn_blocks.py, 100k x 1M: 2 -> 157 ms, 4 -> 155, 8 -> 161, 16 -> 194) expose a
+    quarter of the key copy.  `blocks` given: that many equal blocks."""
+    total = hi - lo
+    if blocks is not None:
+        blocks = max(1, min(blocks, total))
+        return [lo + total * b // blocks for b in range(blocks + 1)]
+    bounds, size = [lo], _PIPELINE_FIRST_KEYS
+    while len(bounds) < _PIPELINE_BLOCKS and hi - bounds[-1] > 2 * size:
+        bounds.append(bounds[-1] + size)
+        size *= _PIPELINE_GROWTH
+    bounds.append(hi)
+    return bounds
 
 
 def normalize_queries_sharded(query_feature, device, world: int, rank: int, process_group=None) -> torch.Tensor:
@@ -171,9 +185,8 @@ def _search_host_keys_pipelined(q32, host_keys, lo, hi, k, mode, device, blocks=
     the same order the shard merge uses, so the result equals the one-shot search bit for bit.  Hides the
     host->device copy of the key set (3 GB for 1M x 768 float32) behind the tensor-core screen.
     Returned indices are index_base + the row number inside host_keys."""
-    blocks = _pipeline_blocks(hi - lo) if blocks is None else blocks
-    blocks = max(1, min(blocks, hi - lo))
-    bounds = [lo + (hi - lo) * b // blocks for b in range(blocks + 1)]
+    bounds = _pipeline_bounds(lo, hi, blocks)
+    blocks = len(bounds) - 1
     longest = max(bounds[b + 1] - bounds[b] for b in range(blocks))
     cur = torch.cuda.current_stream(device)
     copy_stream = torch.cuda.Stream(device=device)

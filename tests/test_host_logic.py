@@ -124,6 +124,12 @@ def _w2_worker(rank, world, store, ret, operands):
                        tensor_core_operands=operands)
     mod2(feats2[0], feats2[1], feats2[2], torch.from_numpy(g.labels[sl].copy()), g.logit_scale).backward()
     out["image_nograd_gather"] = feats2[0].grad.numpy().tolist()
+    # the public gather helper (loss_func.py:73-106) on CPU tensors: the reference's collectives
+    for with_grad in (True, False):
+        x = (torch.arange(12, dtype=torch.float32).reshape(3, 4) + 100 * rank).requires_grad_(True)
+        allf = cb.gather_features(x, local_loss=False, gather_with_grad=with_grad, rank=rank, world_size=world)
+        (allf * (rank + 1)).sum().backward()
+        out[f"gather_{with_grad}"] = (allf.detach().numpy().tolist(), x.grad.numpy().tolist())
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -148,3 +154,9 @@ def test_world2_gloo_orchestration_matches_reference_golden(operands):
         half = np.asarray(ret[r]["image_nograd_gather"], dtype=np.float32)
         ref = g.outputs[f"rank{r}_grad_image"] / world
         assert np.linalg.norm(half - ref) / np.linalg.norm(ref) < 2e-5
+        if operands is None:
+            full = np.concatenate([np.arange(12, dtype=np.float32).reshape(3, 4) + 100 * q for q in range(world)])
+            for with_grad, gsum in ((True, sum(q + 1 for q in range(world))), (False, r + 1)):
+                vals, grad = ret[r][f"gather_{with_grad}"]
+                assert np.array_equal(np.asarray(vals, dtype=np.float32), full)
+                assert np.array_equal(np.asarray(grad, dtype=np.float32), np.full((3, 4), gsum, dtype=np.float32))

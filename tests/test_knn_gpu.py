@@ -125,7 +125,7 @@ def test_host_keys_pipelined_search_equals_one_shot(monkeypatch, pinned):
     q32, k32 = R.normalize_rows(q, dev), R.normalize_rows(keys, dev)
     s_all, i_all, _ = R.search_normalized(q32, k32, 5, mode="fp16")
     monkeypatch.setattr(R, "_PIPELINE_MIN_KEYS", 1)
-    monkeypatch.setattr(R, "_PIPELINE_BLOCK_KEYS", 1000)  # 4003 keys -> 4 blocks
+    monkeypatch.setattr(R, "_PIPELINE_FIRST_KEYS", 500)  # 4003 keys -> blocks of 500, 1000, 2503
     host = torch.from_numpy(keys)
     if pinned:
         host = host.pin_memory()

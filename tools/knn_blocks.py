@@ -1,4 +1,5 @@
-"""kNN end-to-end time (host-resident keys, block-pipelined copy) for several block counts."""
+"""kNN end-to-end time (host-resident keys, block-pipelined copy) for several block counts (0 = the default:
+geometrically growing blocks)."""
 import os
 import sys
 
@@ -14,9 +15,8 @@ cent = torch.randn(50_000, d, device=dev, generator=gen) / d ** 0.5
 keys = (cent[torch.randint(0, 50_000, (K,), device=dev, generator=gen)] + 0.02 * torch.randn(K, d, device=dev, generator=gen)).cpu().pin_memory()
 q = (cent[torch.randint(0, 50_000, (Q,), device=dev, generator=gen)] + 0.02 * torch.randn(Q, d, device=dev, generator=gen)).cpu().pin_memory()
 del cent
-for blocks in [int(a) for a in sys.argv[1:]] or [4, 8, 16]:
-    R._PIPELINE_BLOCKS = blocks
-    R._search_host_keys_pipelined.__defaults__ = (blocks, 0)
+for blocks in [int(a) for a in sys.argv[1:]] or [0, 4, 8]:
+    R._search_host_keys_pipelined.__defaults__ = (blocks or None, 0)
     for it in range(3):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -76,6 +76,31 @@ def main():
                   flush=True)
     os.environ.pop("CLIBD_SHARD_MODE", None)
 
+    # ---- gather_features (loss_func.py:73-106): the peer-memory form against torch's collectives, values and gradients
+    # (gather_with_grad: reduce-scatter(SUM) of the gathered gradient; without: only the local rows carry a gradient)
+    for dtype, n, d in ((torch.float32, 130, 96), (torch.bfloat16, 257, 768)):
+        gen = torch.Generator().manual_seed(100 + rank)
+        x = torch.randn(n, d, generator=gen).to(dtype).to(dev)
+        wgt = torch.randn(n * world, d, generator=torch.Generator().manual_seed(7)).to(dtype).to(dev) * (1 + rank)
+        for with_grad in (True, False):
+            res = {}
+            for form in ("nccl", "peer"):
+                os.environ["CLIBD_SHARD_MODE"] = form
+                for it in range(2):  # the second call reuses the receive buffer
+                    leaf = x.clone().requires_grad_(True)
+                    allf = cb.gather_features(leaf, local_loss=False, gather_with_grad=with_grad, rank=rank,
+                                              world_size=world)
+                    (allf.float() * wgt.float()).sum().backward()
+                res[form] = (allf.detach().clone(), leaf.grad.clone())
+            os.environ.pop("CLIBD_SHARD_MODE", None)
+            good = bool(torch.equal(res["peer"][0], res["nccl"][0]))
+            gerr = float((res["peer"][1].float() - res["nccl"][1].float()).abs().max() / res["nccl"][1].float().abs().max())
+            gtol = 0.0 if not with_grad else (1e-6 if dtype == torch.float32 else 2e-2)  # NCCL's own summation order
+            good = good and gerr <= gtol and bool(torch.equal(allf[rank * n:(rank + 1) * n], x))
+            ok &= good
+            print(f"[rank {rank}] gather_features {str(dtype)[6:]} n={n} with_grad={with_grad}: values equal, "
+                  f"rel grad diff {gerr:.2e}: {'OK' if good else 'FAIL'}", flush=True)
+
     # ---- kNN: sharded keys + all-gather + merge == unsharded
     Q, K, d, k = 700, 20011, 768, 5
     gen = torch.Generator().manual_seed(5)
