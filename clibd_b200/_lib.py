@@ -14,7 +14,7 @@ _I64 = _c.c_int64
 _INT = _c.c_int
 _F = _c.c_float
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 DT_F32, DT_BF16, DT_F16, DT_F64 = 0, 1, 2, 3
 MODE_LOCAL, MODE_EXCHANGE = 0, 1
 PATH_SIMT_F32, PATH_TC_BF16, PATH_TC_F16 = 0, 1, 2
@@ -43,6 +43,8 @@ SIGNATURES = {
     "clibd_shard_push_stats": (_INT, [_P, _P, _I64, _I64, _I64, _INT, _INT, _P, _P, _P, _P]),
     "clibd_shard_reduce_stats": (_INT, [_P, _P, _I64, _INT, _P, _P, _P]),
     "clibd_shard_push_floats": (_INT, [_P, _I64, _INT, _INT, _P, _P]),
+    "clibd_shard_barrier": (_INT, [_P, _INT, _INT, _INT, _P]),
+    "clibd_shard_barrier_bytes": (_I64, []),
     "clibd_knn_normalize": (_INT, [_P, _INT, _I64, _I64, _P, _P]),
     "clibd_knn_scratch_bytes": (_I64, [_I64, _I64, _I64, _INT, _INT]),
     "clibd_knn_search": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _INT, _INT, _P, _I64, _P, _P, _P, _P]),

@@ -11,7 +11,8 @@ Layout of one pool ENTRY (everything a forward hands to its backward; identical 
     colslots  [W, 3, N] float32 column-sum partials per rank  posslots [W, 4] float64, pos_local / pos [4] float64
 and of the per-configuration SHARED block (two parities, alternating per backward):
     red       [3 pairs, W, n, d] float32 column-side gradient partials received from every rank
-    gslots    [W] float32 grad_output of every rank
+    gslots    [W] float32 grad_output of every rank        dslots  [W] float64 d loss / d logit_scale of every rank
+    flags     clibd_shard_barrier's epochs (not duplicated: they only grow)
 
 Why a single entry is enough in a training loop, and when the pool grows: a rank writes into its peers' entry only
 at the start of a forward (rows) and after the first barrier of that forward (statistics); its peers read those
@@ -22,6 +23,9 @@ outstanding keeps its entry; a second forward then takes (or allocates, collecti
 alternate between two copies because two backward passes may follow each other without a forward in between.
 """
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 
@@ -116,8 +120,15 @@ class PeerContext:
         self.red_pair_bytes = 4 * world * n * d  # one pair's slot array [W, n, d]
         red_bytes = _align(3 * self.red_pair_bytes)
         g_off = 2 * red_bytes
-        self.shared = _Region(g_off + 2 * 256, device, group)
+        d_off = g_off + 2 * 256                # dslots [2 parities][W] float64: every rank's d loss / d logit_scale
+        flag_off = d_off + 2 * _align(8 * world)
+        self.shared = _Region(flag_off + _align(_lib.load().clibd_shard_barrier_bytes()), device, group)
         base = self.shared.ptrs
+        self.peer_dslots = [_lib.ptr_array([base[q] + d_off + par * _align(8 * world) for q in range(world)])
+                            for par in range(2)]
+        self.dslots = [self.shared.tensor[d_off + par * _align(8 * world):d_off + par * _align(8 * world) + 8 * world]
+                       .view(torch.float64) for par in range(2)]
+        self.peer_flags = _lib.ptr_array([base[q] + flag_off for q in range(world)])  # clibd_shard_barrier's blocks
         self.red_ptr = [base[rank] + par * red_bytes for par in range(2)]
         self.gslots_ptr = [base[rank] + g_off + par * 256 for par in range(2)]
         # entry [q * 3 + p]: pair p's slot array inside rank q's memory
@@ -127,8 +138,15 @@ class PeerContext:
 
     def barrier(self, channel=0):
         """All ranks' earlier work on the current stream (incl. their stores into peer memory) is complete and visible
-        before any rank's later work starts.  Barriers issued on two streams at once use different channels."""
-        self.shared.handle.barrier(channel=channel)
+        before any rank's later work starts.  Barriers issued on two streams at once use different channels.
+        Default: torch's symmetric-memory barrier.  CLIBD_BARRIER=own: this library's one-warp kernel over flags in the
+        shared region (clibd_shard_barrier, csrc/shard_exchange.cu) -- what a host without torch would call; the two cost
+        the same (tools/barrier_probe.py, 2 GPUs: 6.4 vs 6.2 us back to back, 11.5 vs 9.4 us with a kernel in between)."""
+        if os.environ.get("CLIBD_BARRIER", "torch") != "own":
+            self.shared.handle.barrier(channel=channel)
+            return
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.load().clibd_shard_barrier(self.peer_flags, self.rank, self.world, channel, stream))
 
     def side_stream(self):
         """Second stream of the forward: the push of the feature rows runs there, next to the label statistics."""

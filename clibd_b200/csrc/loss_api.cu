@@ -248,6 +248,9 @@ LossPlan make_loss_plan(int64_t N, int64_t n, int64_t d, int path, bool allow_sh
         p.off_gt = take(2 * static_cast<size_t>(n) * p.gt_ld);
         // sharded step: (image, text) and (dna, text) feed ONE gradient GEMM, each from its own strip
         p.off_gt2 = p.exchange ? take(2 * static_cast<size_t>(n) * p.gt_ld) : p.off_gt;
+        // ... and a third one, so that the gradient GEMM of (image, dna) can still read its strip while the sweeps of
+        // the two text pairs fill theirs (shared_s_sweeps: GEMM on the side stream next to the following sweeps)
+        p.off_gt3 = p.exchange ? take(2 * static_cast<size_t>(n) * p.gt_ld) : p.off_gt;
         p.npad_loc = round_up(n, 8);
         for (int m = 0; m < 3; ++m) {
             p.off_xhTo[m] = take(2 * static_cast<size_t>(p.dpad) * p.npad_loc);
@@ -419,8 +422,20 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
         if (g < 0) g = ngroups++;
         group_pairs[g][group_size[g]++] = p;
     }
-    void* gts[2] = {gt, at<void>(scratch, plan.off_gt2)};
+    // Sharded step: a rank's sweep runs 2 x n / 128 x jsplit CTAs -- 128 of 148 SMs at n = 4096 -- and the gradient GEMM
+    // of a group only needs that group's strips.  With one strip per pair (the whole column range fits) the GEMM of every
+    // group but the last therefore goes to the side stream, where its CTA pairs fill the SMs the following sweeps leave
+    // idle and its epilogue's NVLink stores spread over a longer time; the groups then use disjoint strip buffers.
+    // CLIBD_OVERLAP_GEMM=0 keeps everything in line.
+    void* bufs[3] = {gt, at<void>(scratch, plan.off_gt2), at<void>(scratch, plan.off_gt3)};
+    const char* ov_env = std::getenv("CLIBD_OVERLAP_GEMM");
+    const bool overlap_gemm = plan.exchange && side != nullptr && ngroups > 1 && plan.strip_rows >= N &&
+                              !(ov_env != nullptr && std::atoi(ov_env) == 0);
+    int buf0 = 0;
     for (int g = 0; g < ngroups; ++g) {
+        void* gts[2] = {bufs[overlap_gemm ? buf0 : 0], bufs[overlap_gemm ? buf0 + 1 : 1]};
+        buf0 += group_size[g];
+        cudaStream_t gemm_stream = stream;
         const int p0 = group_pairs[g][0];
         const int b = kPairB[p0];
         GradDest dest;
@@ -464,8 +479,16 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
                 parts[k].gs = gts[k];
                 parts[k].xhT_x = at<void>(scratch, plan.off_xhTo[a]);
             }
+            if (overlap_gemm && g + 1 < ngroups) {
+                if ((rc = side_fork(side, stream))) return rc;  // after this group's sweeps; joined at the end
+                gemm_stream = side->stream;
+            } else if (overlap_gemm && acc_grad) {
+                // accumulates onto what an earlier group's GEMM (possibly still running on the side stream) wrote
+                if ((rc = side_join(side, stream))) return rc;
+            }
             if ((rc = tc_grad_from_strip(parts, group_size[g], plan.gt_ld, c1 - c0, c0, n, plan.npad_loc, N, d, plan.dpad, sidx,
-                                         gscale, pair_weight[p0], acc_grad, ksplit, fmt_bf16, dest, tc_num_sms(), stream)))
+                                         gscale, pair_weight[p0], acc_grad, ksplit, fmt_bf16, dest, tc_num_sms(),
+                                         gemm_stream)))
                 return rc;
         }
         for (int k = 0; k < group_size[g]; ++k) wrote_dxh[kPairA[group_pairs[g][k]]] = true;
@@ -993,6 +1016,8 @@ static GraphKey base_key(int tag, const void* const x[3], int dtype, const float
     k.add(plan.total).add(plan.jsplit).add(plan.shared_s).add(plan.strip_rows).add(plan.bwd_single);
     const char* side_env = std::getenv("CLIBD_SIDE_STREAM");
     k.add(side_env != nullptr && std::atoi(side_env) == 0);  // the captured sequence forks a side stream or does not
+    const char* ov_env = std::getenv("CLIBD_OVERLAP_GEMM");
+    k.add(ov_env != nullptr && std::atoi(ov_env) == 0);
     return k;
 }
 

@@ -47,7 +47,7 @@ struct LossPlan {
     bool shared_s = false;
     bool exchange = false;
     int64_t strip_rows = 0, gt_ld = 0, npad_loc = 0;
-    size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0, off_gt2 = 0;  // gt2: second strip (merged pairs)
+    size_t off_xhTo[3] = {0, 0, 0}, off_Qw[3] = {0, 0, 0}, off_gt = 0, off_gt2 = 0, off_gt3 = 0;  // gt2, gt3: further strips (sharded step)
     size_t off_u = 0, off_v = 0, off_rowpart = 0, off_colpart = 0, off_posrow = 0, off_dots = 0;
     size_t off_red = 0;  // small double buffer for block reductions
     // label hash table (own/min/count per slot), rows sorted by class (keys, indices), sort input and CUB scratch

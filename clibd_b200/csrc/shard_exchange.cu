@@ -8,6 +8,7 @@
 //   clibd_shard_push_stats   first half of the statistics all-reduce: disjoint segments in place, column-sum
 //   clibd_shard_reduce_stats partials into per-rank slots, summed in rank order after the caller's barrier
 //   clibd_shard_push_floats  small per-rank slot vectors (each rank's grad_output)
+//   clibd_shard_barrier      barrier across the ranks on the caller's stream (flags in peer-mapped memory)
 //
 // (the reduce-scatter of the column-side gradients is not here: the gradient GEMM's epilogue stores its rows straight
 //  into the owners' slot arrays, loss_grad_gemm.cu.)  Writers and readers are separated by a barrier across the ranks
@@ -127,6 +128,47 @@ __global__ void shard_push_floats_kernel(const float* __restrict__ src, int64_t 
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+constexpr int kBarrierChannels = 4;
+static_assert(MAX_PEERS <= 32, "one warp signals and waits for all peers");
+
+struct PeerFlags {
+    unsigned long long* f[MAX_PEERS];  // rank q's block: [channel][writer rank] epochs, then [channel] own epoch counter
+};
+
+// Barrier across the ranks, one warp: lane q stores this rank's new epoch of the channel into rank q's block (release,
+// system scope: everything earlier kernels of this stream wrote -- into peer memory too -- is visible to whoever
+// acquires the flag) and then waits until rank q's epoch has arrived in its own block.  Epochs only grow and every
+// (writer, reader) slot has one writer, so nothing is ever reset, and a rank that is a whole barrier ahead is harmless.
+// The epoch counter lives in device memory: the kernel takes no per-call argument and can be replayed from a CUDA graph.
+__global__ void shard_barrier_kernel(PeerFlags peers, int rank, int world, int channel) {
+    unsigned long long* mine = peers.f[rank];
+    unsigned long long* counter = mine + kBarrierChannels * MAX_PEERS + channel;
+    const int q = threadIdx.x;
+    unsigned long long epoch = 0;
+    if (q == 0) {
+        epoch = *counter + 1;
+        *counter = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
+    if (q < world) {
+        __threadfence_system();
+        unsigned long long* theirs = peers.f[q] + channel * MAX_PEERS + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+        const unsigned long long* slot = mine + channel * MAX_PEERS + q;
+        unsigned long long seen = 0;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(slot) : "memory");
+            if (seen >= epoch) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 60ull * 1000000000ull) __trap();  // a peer never arrived: fail instead of hanging the GPU
+            __nanosleep(64);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace clibd
 
@@ -222,6 +264,24 @@ int clibd_shard_push_floats(const float* src, int64_t count, int rank, int world
     shard_push_floats_kernel<<<grid, kThreads, 0, stream>>>(src, count, rank, peers);
     CLIBD_KERNEL_CHECK();
     return 0;
+}
+
+int clibd_shard_barrier(uint64_t* const peer_flags[], int rank, int world, int channel, clibd_stream_t stream) {
+    CLIBD_REQUIRE(peer_flags && world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world && channel >= 0 &&
+                      channel < kBarrierChannels,
+                  "bad arguments");
+    PeerFlags peers;
+    for (int q = 0; q < MAX_PEERS; ++q) {
+        peers.f[q] = q < world ? reinterpret_cast<unsigned long long*>(peer_flags[q]) : nullptr;
+        if (q < world) CLIBD_REQUIRE(peer_flags[q] != nullptr, "null peer flag block");
+    }
+    shard_barrier_kernel<<<1, 32, 0, stream>>>(peers, rank, world, channel);
+    CLIBD_KERNEL_CHECK();
+    return 0;
+}
+
+int64_t clibd_shard_barrier_bytes(void) {
+    return sizeof(unsigned long long) * (kBarrierChannels * MAX_PEERS + kBarrierChannels);
 }
 
 }  // extern "C"

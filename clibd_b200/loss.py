@@ -319,6 +319,7 @@ class _FusedClipLossFn(torch.autograd.Function):
             outs = _lib.ptr_array3([None if g is None else g.data_ptr() for g in dxs])
             w = _lib.float_array3(weights)
             sp, sn = ctx.scratch.data_ptr(), ctx.scratch.numel()
+            want_dscale = ctx.has_scale and ctx.needs_input_grad[4]  # else nobody reads it: no exchange over the ranks
             # grad_output stays on the device: the library multiplies it into the feature gradients.  Backward of the
             # differentiable all-gather = reduce-scatter(SUM) over ranks (loss_func.py:97): every rank's loss is the same
             # function, so the local rows receive (sum_r grad_output_r) * dL/dx.
@@ -339,7 +340,10 @@ class _FusedClipLossFn(torch.autograd.Function):
                 _lib.check(lib.clibd_loss_backward_finish(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn,
                                                           reduced, _lib.int_array(count), 1.0, g_ptr, g_count, outs,
                                                           dscale.data_ptr(), stream))
-                dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
+                if want_dscale:  # dL/ds needs all rows: every rank's share into per-rank slots, summed in rank order
+                    _lib.check(lib.clibd_shard_push_floats(dscale.data_ptr(), 2, rank, world, px.peer_dslots[par], stream))
+                    px.barrier()
+                    dscale = px.dslots[par].sum().reshape(1)
                 holder.release()
             elif shard == "nccl":
                 gsum = grad_out
@@ -357,7 +361,8 @@ class _FusedClipLossFn(torch.autograd.Function):
                                                           _lib.ptr_array3([None if t is None else t.data_ptr() for t in reduced]),
                                                           _lib.int_array([0 if t is None else 1 for t in reduced]), 1.0,
                                                           gsum.data_ptr(), 1, outs, dscale.data_ptr(), stream))
-                dist.all_reduce(dscale, group=group)
+                if want_dscale:
+                    dist.all_reduce(dscale, group=group)
             else:
                 gsum = grad_out
                 if world > 1 and sum_grads:
@@ -365,11 +370,11 @@ class _FusedClipLossFn(torch.autograd.Function):
                     dist.all_reduce(gsum, group=group)
                 _lib.check(lib.clibd_loss_backward(xs, _DT[dtype], ivs, N, d, row0, n, scale_value, w, path, sp, sn, 1.0,
                                                    gsum.data_ptr(), outs, dscale.data_ptr(), stream))
-                if world > 1:
+                if world > 1 and want_dscale:
                     dist.all_reduce(dscale, group=group)  # dL/ds needs all rows
             grads = dxs
             gscale = None
-            if ctx.has_scale and ctx.needs_input_grad[4]:
+            if want_dscale:
                 gscale = (dscale[0] * grad_out[0].double()).to(ctx.scale_dtype).reshape(())
         return grads[0], grads[1], grads[2], None, gscale, None, None, None, None, None, None, None
 

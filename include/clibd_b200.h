@@ -35,7 +35,7 @@ extern "C" {
 
 typedef struct CUstream_st* clibd_stream_t; /* == cudaStream_t */
 
-#define CLIBD_ABI_VERSION 6
+#define CLIBD_ABI_VERSION 7
 
 int clibd_abi_version(void);
 const char* clibd_last_error(void);
@@ -185,6 +185,14 @@ int clibd_shard_reduce_stats(const float* colslots, const double* posslots, int6
  * ([world, count] float32) -- e.g. each rank's autograd grad_output, summed by clibd_loss_backward_finish. */
 int clibd_shard_push_floats(const float* src, int64_t count, int rank, int world, float* const peer_slots[] /* host */,
                             clibd_stream_t stream);
+/* clibd_shard_barrier: barrier across the ranks on `stream` -- everything the ranks enqueued before it (their stores
+ * into peer memory included) is complete and visible before anything enqueued after it starts.  peer_flags[q] = rank
+ * q's flag block of clibd_shard_barrier_bytes() bytes in peer-mapped memory, zeroed once before first use; barriers that
+ * may be in flight at the same time (two streams) use different channels (0..3).  Replaces the NCCL collective's implicit
+ * synchronisation of torch.distributed.nn.all_gather (loss_func.py:97,143) in the peer form of the sharded step; takes no
+ * per-call state from the host, so it can sit inside a CUDA graph.  A peer that never arrives traps after 60 s. */
+int clibd_shard_barrier(uint64_t* const peer_flags[] /* host */, int rank, int world, int channel, clibd_stream_t stream);
+int64_t clibd_shard_barrier_bytes(void);
 
 /* ---- cosine nearest-neighbour retrieval --------------------------------------------
  * Replaces make_prediction / find_closest_match's search (bioscanclip/util/util.py:

@@ -234,6 +234,51 @@ def test_side_stream_overlap_is_bit_identical(monkeypatch):
             assert np.array_equal(a, b)
 
 
+def test_gradient_gemm_on_the_side_stream_is_bit_identical(monkeypatch):
+    """The gradient GEMM of the first pair group runs on the side stream next to the following sweeps, each group with
+    its own strip buffer (loss_api.cu: shared_s_sweeps); in line (CLIBD_OVERLAP_GEMM=0) it must give the same bits."""
+    from clibd_b200 import _lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4)
+    N, d, world = 4096, 768, 4
+    feats = [torch.randn(N, d, generator=gen).bfloat16().to(dev) for _ in range(3)]
+    labels = torch.randint(0, N // 8, (N,), generator=gen).to(dev)
+    for form in ("peer", "reduce_scatter"):
+        monkeypatch.setenv("CLIBD_OVERLAP_GEMM", "0")
+        ref = _sharded_step(feats, labels, 1 / 0.07, world, _lib.PATH_TC_BF16, form)
+        monkeypatch.setenv("CLIBD_OVERLAP_GEMM", "1")
+        for rep in range(3):
+            got = _sharded_step(feats, labels, 1 / 0.07, world, _lib.PATH_TC_BF16, form)
+            assert got[0] == ref[0] and got[2] == ref[2]
+            for a, b in zip(got[1], ref[1]):
+                assert np.array_equal(a, b)
+
+
+def test_barrier_kernel_single_rank_epochs():
+    """clibd_shard_barrier with world = 1 (the rank signals itself): the per-channel epoch counters advance, the flag
+    slots follow, channels are independent.  Ranks that wait for each other cannot be simulated with streams of ONE
+    GPU -- two streams may share a hardware queue, where the kernel behind a spinning barrier is never dispatched --
+    so the multi-rank behaviour is checked on real GPUs (tools/multigpu_check.py runs every exchange through it)."""
+    from clibd_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    words = lib.clibd_shard_barrier_bytes() // 8
+    assert words == 4 * 16 + 4
+    block = torch.zeros(words, dtype=torch.int64, device=dev)
+    flags = _lib.ptr_array([block.data_ptr()])
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for _ in range(5):
+        _lib.check(lib.clibd_shard_barrier(flags, 0, 1, 0, sp))
+    for _ in range(2):
+        _lib.check(lib.clibd_shard_barrier(flags, 0, 1, 3, sp))
+    torch.cuda.synchronize()
+    host = block.cpu()
+    assert int(host[4 * 16 + 0]) == 5 and int(host[0]) == 5          # channel 0: counter and the slot rank 0 wrote
+    assert int(host[4 * 16 + 3]) == 2 and int(host[3 * 16]) == 2      # channel 3
+    assert int(host[4 * 16 + 1]) == 0 and int(host[1]) == 0           # nobody else was touched
+    assert lib.clibd_shard_barrier(flags, 1, 1, 0, sp) != 0 and lib.clibd_shard_barrier(flags, 0, 1, 4, sp) != 0
+
+
 @pytest.mark.parametrize("bind_to,no_it,weights", [
     ("image", False, (0.25, 0.25, 0.0)),   # bind_to="image": (image,dna) and (image,text); text's only column pair is pair 1
     (None, True, (0.25, 0.0, 0.25)),       # no_image_text_loss: (image,dna) and (dna,text); text's column pair is pair 2

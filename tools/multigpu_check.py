@@ -36,8 +36,9 @@ def main():
              (333, 768, 2, torch.float16, None, 2e-3),
              (1024, 768, 3, torch.float32, "bf16", 1e-3),  # fp32 leaves: no output rounding
              (2048, 768, 3, torch.float32, "fp16", 1e-3)]
-    for shard_mode in ("local", "nccl", "peer"):
-        os.environ["CLIBD_SHARD_MODE"] = shard_mode
+    for shard_mode in ("local", "nccl", "peer", "peer+own_barrier"):
+        os.environ["CLIBD_SHARD_MODE"] = shard_mode.split("+")[0]
+        os.environ["CLIBD_BARRIER"] = "own" if shard_mode.endswith("own_barrier") else "torch"  # clibd_shard_barrier
         for (n, d, nmod, dtype, operands, tol) in cases:
             N = n * world
             gen = torch.Generator().manual_seed(11)
@@ -71,10 +72,11 @@ def main():
             e_ds = abs(float(scale.grad) - g_out * float(scale_full.grad)) / abs(g_out * float(scale_full.grad))
             good = e_loss < 1e-5 and max(errs) < tol and e_ds < 1e-3
             ok &= good
-            print(f"[rank {rank}] {shard_mode:5s} loss n={n} d={d} nmod={nmod} {str(dtype)[6:]} operands={operands}: "
+            print(f"[rank {rank}] {shard_mode:16s} loss n={n} d={d} nmod={nmod} {str(dtype)[6:]} operands={operands}: "
                   f"loss_err={e_loss:.2e} grad_err={max(errs):.2e} dscale_err={e_ds:.2e} {'OK' if good else 'FAIL'}",
                   flush=True)
     os.environ.pop("CLIBD_SHARD_MODE", None)
+    os.environ.pop("CLIBD_BARRIER", None)
 
     # ---- gather_features (loss_func.py:73-106): the peer-memory form against torch's collectives, values and gradients
     # (gather_with_grad: reduce-scatter(SUM) of the gathered gradient; without: only the local rows carry a gradient)
