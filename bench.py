@@ -289,12 +289,15 @@ def run_ours(args):
         module = cb.ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world)
     else:
         module = cb.ContrastiveLoss(None, 1 / 0.07)
-    scale = torch.tensor(1 / 0.07, device=dev)
+    # a learnable logit scale, as in training (simple_clip.py:32,61) and in the reference arm above: d loss / d logit_scale
+    # is part of the step (on several GPUs it is exchanged over the ranks)
+    scale = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
     resident = [h.to(dev) for h in host]
     resident_labels = host_labels.to(dev)
 
     def step_resident():
         leaves = [r.detach().requires_grad_(True) for r in resident]
+        scale.grad = None  # optimizer.zero_grad(set_to_none=True)
         loss = module(leaves[0], leaves[1], leaves[2], resident_labels, scale)
         loss.backward()
         return loss
@@ -342,6 +345,7 @@ def run_ours(args):
         stream.wait_event(cur["ready"])
         issue_copy(nxt)
         leaves = [f.detach().requires_grad_(True) for f in cur["feats"]]
+        scale.grad = None
         loss = module(leaves[0], leaves[1], leaves[2], cur["labels"], scale)
         loss.backward()
         cur["free"] = stream.record_event()
@@ -460,8 +464,11 @@ def run_ours(args):
         "roofline_fwd": roofline_fwd, "roofline_grad": roofline_grad, "step_tensor_frac_algorithmic": step_frac,
         # the same 18*n*N*d algorithmic flops of the whole step against the burst cuBLAS figure, for reference
         "step_tensor_frac_algorithmic_vs_burst": (step_frac * peak_tf / burst_tf) if burst_tf else None,
-        # what is not tensor-kernel time: staging, statistics, exchanges between the ranks, launch gaps
-        "step_fixed_ms": ms_step - tensor_ms,
+        # what is not tensor-kernel time: staging, statistics, launch gaps.  One GPU only: in the sharded step a gradient
+        # GEMM runs on a second stream next to the following sweeps, so the kernels' durations no longer add up to a share
+        # of the step (and each is longer than it would be alone: the per-kernel rooflines are quoted at N = 1)
+        "step_fixed_ms": (ms_step - tensor_ms) if world == 1 else None,
+        "tensor_kernels_overlap": world > 1 and os.environ.get("CLIBD_OVERLAP_GEMM", "1") != "0",
         "cuda_graphs": graphs,
         "ms_per_step_with_kernel_events": ms_profiled_total / args.steps,
         "shard_exchange": (os.environ.get("CLIBD_SHARD_MODE") or "peer (default)") if world > 1 else None,
@@ -505,7 +512,7 @@ def config1_latency(torch, cb, dev):
     b = torch.randn(256, DIM, generator=gen).to(dev)
     labels = torch.arange(256, device=dev)
     mod = cb.ContrastiveLoss(None, 1 / 0.07)
-    scale = torch.tensor(1 / 0.07, device=dev)
+    scale = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
     out = {}
     for name, operands in (("fp32_exact_path", None), ("bf16_tensor_core_path", "bf16")):
         mod.tensor_core_operands = operands
@@ -514,6 +521,7 @@ def config1_latency(torch, cb, dev):
             la, lb = a.detach().requires_grad_(True), b.detach().requires_grad_(True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            scale.grad = None
             mod(la, lb, None, labels, scale).backward()
             e1.record()
             e1.synchronize()

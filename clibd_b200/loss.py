@@ -375,7 +375,7 @@ class _FusedClipLossFn(torch.autograd.Function):
             grads = dxs
             gscale = None
             if want_dscale:
-                gscale = (dscale[0] * grad_out[0].double()).to(ctx.scale_dtype).reshape(())
+                gscale = (dscale * grad_out).to(ctx.scale_dtype).reshape(())  # float64 x float32 -> float64 product, one kernel
         return grads[0], grads[1], grads[2], None, gscale, None, None, None, None, None, None, None
 
 
