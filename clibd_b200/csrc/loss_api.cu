@@ -433,7 +433,7 @@ static int shared_s_sweeps(const void* const x[3], int dtype, const float* const
                               !(ov_env != nullptr && std::atoi(ov_env) == 0);
     int buf0 = 0;
     for (int g = 0; g < ngroups; ++g) {
-        void* gts[2] = {bufs[overlap_gemm ? buf0 : 0], bufs[overlap_gemm ? buf0 + 1 : 1]};
+        void* gts[2] = {bufs[overlap_gemm ? buf0 : 0], bufs[overlap_gemm ? (buf0 + 1 < 3 ? buf0 + 1 : 2) : 1]};  // [1]: merged groups only
         buf0 += group_size[g];
         cudaStream_t gemm_stream = stream;
         const int p0 = group_pairs[g][0];

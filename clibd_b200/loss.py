@@ -312,7 +312,11 @@ class _FusedClipLossFn(torch.autograd.Function):
         stream = _stream_ptr(device)
         with _device_ctx(device):
             grad_out = grad_out.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
-            dxs = [torch.empty((n, d), dtype=dtype, device=device) if (p and ctx.needs_input_grad[i]) else None
+            # a modality that is present but in no weighted pair (bind_to + no_image_text_loss can leave one out) gets no
+            # gradient, as in the reference, where it never enters the graph
+            used = (weights[0] != 0 or weights[1] != 0, weights[0] != 0 or weights[2] != 0,
+                    weights[1] != 0 or weights[2] != 0)
+            dxs = [torch.empty((n, d), dtype=dtype, device=device) if (p and used[i] and ctx.needs_input_grad[i]) else None
                    for i, p in enumerate(ctx.present)]
             dscale = torch.zeros(1, dtype=torch.float64, device=device)
             xs, ivs = _lib.ptr_array3(ctx.x_ptrs), _lib.ptr_array3(ctx.inv_ptrs)

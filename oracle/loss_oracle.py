@@ -111,7 +111,10 @@ def contrastive_loss(features, labels, logit_scale, bind_to=None, no_image_text_
             ds += float((dS_ab * cos_ab).sum() + (dS_ba * cos_ba).sum())
     out = {"loss": total / n_terms, "grads": [None, None, None], "dlogit_scale": None}
     if want_grad:
+        in_a_pair = {k for ab in pairs for k in ab}
         for k, i in enumerate(present):
+            if k not in in_a_pair:
+                continue  # a modality no pair uses never enters the reference's graph: its leaf keeps grad None
             x_hat, nrm = normed[k]
             dot = (x_hat * dxh[k]).sum(axis=1, keepdims=True)
             out["grads"][i] = (dxh[k] - x_hat * dot) / nrm
@@ -176,7 +179,10 @@ def contrastive_loss_streaming(features, labels, logit_scale, bind_to=None, no_i
                 ds += float((G * cos).sum())
     out = {"loss": total / n_terms, "grads": [None, None, None], "dlogit_scale": None}
     if want_grad:
+        in_a_pair = {k for ab in pairs for k in ab}
         for k, i in enumerate(present):
+            if k not in in_a_pair:
+                continue  # as in contrastive_loss: no pair, no gradient
             x_hat, nrm = normed[k]
             dot = (x_hat * dxh[k]).sum(axis=1, keepdims=True)
             out["grads"][i] = (dxh[k] - x_hat * dot) / nrm

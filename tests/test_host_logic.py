@@ -88,7 +88,9 @@ def test_single_process_orchestration_with_double_matches_golden():
             (loss * g.meta.get("grad_mult", 1.0)).backward()
             assert float(loss) == pytest.approx(float(g.outputs["loss"]), rel=2e-6)
             for f, m in zip(feats, _golden.MODS):
-                if f is not None:
+                if f is not None and f"grad_{m}" not in g.outputs:
+                    assert f.grad is None, m  # present but in no pair: no gradient, as in the reference
+                elif f is not None:
                     ref = g.outputs[f"grad_{m}"]
                     assert np.linalg.norm(f.grad.numpy() - ref) / np.linalg.norm(ref) < 2e-5
             if "dlogit_scale" in g.outputs:

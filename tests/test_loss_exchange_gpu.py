@@ -143,7 +143,7 @@ def _sharded_step(feats, labels, scale, world, path, form, weights=(1 / 6, 1 / 6
             reduced = [None if f is None else sum(part[q][m][r * n:(r + 1) * n] for q in R).contiguous()
                        for m, f in enumerate(first)]
             slots = [0 if f is None else 1 for f in first]
-        dx = [None if f is None else torch.empty((n, d), dtype=dtype, device=dev) for f in feats]
+        dx = [None if f is None else torch.zeros((n, d), dtype=dtype, device=dev) for f in feats]  # no pair: stays 0
         _lib.check(lib.clibd_loss_backward_finish(
             _lib.ptr_array3([P(t) for t in gx[r]]), dt, _lib.ptr_array3([P(t) for t in ginv[r]]), N, d, r * n, n, 0.0, w,
             path, scratch[r].data_ptr(), nbytes, _lib.ptr_array3([P(t) for t in reduced]), _lib.int_array(slots), 1.0,
@@ -305,3 +305,35 @@ def test_simulated_ranks_pair_filters(bind_to, no_it, weights):
         for i in range(3):
             assert _rel(grads[i], world * ref["grads"][i]) < 1e-3 + 2 ** -8, (form, i)
         assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
+
+
+def test_unequal_pair_weights_are_linear_in_the_pairs(monkeypatch):
+    """Pair weights that differ (only reachable through the C ABI: the reference's pair list always weighs its pairs
+    equally) keep the two text pairs in separate gradient GEMMs that accumulate into one partial buffer -- three pair
+    groups, three strip buffers, the last GEMM joined behind the side-stream ones.  The step is linear in the pair
+    weights, so it must equal the sum of the three single-pair steps."""
+    from clibd_b200 import _lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(21)
+    N, d, world = 1024, 768, 4
+    feats = [torch.randn(N, d, generator=gen).bfloat16().to(dev) for _ in range(3)]
+    labels = torch.randint(0, N // 8, (N,), generator=gen).to(dev)
+    scale = 1 / 0.07
+    w = (0.2, 0.3, 0.5)
+    for ov in ("1", "0"):
+        monkeypatch.setenv("CLIBD_OVERLAP_GEMM", ov)
+        losses, grads, ds = _sharded_step(feats, labels, scale, world, _lib.PATH_TC_BF16, "reduce_scatter", w)
+        loss_sum, ds_sum = 0.0, 0.0
+        grad_sum = [np.zeros((N, d), np.float64) for _ in range(3)]
+        for p in range(3):
+            wp = tuple(w[q] if q == p else 0.0 for q in range(3))
+            l1, g1, d1 = _sharded_step(feats, labels, scale, world, _lib.PATH_TC_BF16, "reduce_scatter", wp)
+            loss_sum += l1[0]
+            ds_sum += d1
+            for i in range(3):
+                if g1[i] is not None:
+                    grad_sum[i] += np.asarray(g1[i], np.float64)
+        assert abs(losses[0] - loss_sum) <= 1e-5 * abs(loss_sum)
+        assert abs(ds - ds_sum) <= 1e-4 * abs(ds_sum)
+        for i in range(3):
+            assert _rel(grads[i], grad_sum[i]) < 1e-2, (ov, i)

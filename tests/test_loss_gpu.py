@@ -26,7 +26,7 @@ def _run(module, feats, labels, scale, grad_mult=1.0, **fw):
         loss = loss["contrastive_loss"]
     (loss * grad_mult).backward()
     torch.cuda.synchronize()
-    return (float(loss), [None if l is None else l.grad.float().cpu().numpy() for l in leaves],
+    return (float(loss), [None if (l is None or l.grad is None) else l.grad.float().cpu().numpy() for l in leaves],
             float(s.grad) if isinstance(s, torch.Tensor) else None)
 
 
@@ -48,6 +48,8 @@ def test_fp32_path_matches_reference_golden(g):
     for i, m in enumerate(_golden.MODS):
         if f"grad_{m}" in g.outputs:
             assert _rel(grads[i], g.outputs[f"grad_{m}"]) < 1e-5, m
+        else:  # absent, or present but in no pair (the reference leaves its .grad None)
+            assert grads[i] is None, m
     if "dlogit_scale" in g.outputs:
         ref = float(g.outputs["dlogit_scale"])
         assert abs(ds - ref) <= 1e-5 * abs(ref) + 1e-7
@@ -111,6 +113,26 @@ def test_tensor_core_path_matches_oracle(operands, N, d, nmod, labels_kind, back
         if ref["grads"][i] is not None:
             # gradients are returned in the input dtype (bf16): allow its rounding on top of 1e-3
             assert _rel(grads[i], ref["grads"][i]) < 1e-3 + 2 ** -8, i
+    assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
+
+
+@pytest.mark.parametrize("N", [512, 4096])
+def test_modality_in_no_pair_gets_no_gradient_tensor_core_path(N):
+    """ClipLoss(bind_to="image", no_image_text_loss=True) with all three modalities: only (image, dna) survives the
+    reference's filters (loss_func.py:166-184); text is staged nowhere and its leaf keeps grad None.  Both backward
+    forms of the tcgen05 path (two sweeps at N = 512, S once per pair at N = 4096) against the oracle."""
+    import clibd_b200 as cb
+    dev = torch.device("cuda:0")
+    feats, labels = _synthetic(N, 768, 3, "multi", seed=31, dtype=torch.bfloat16)
+    scale = torch.tensor(1 / 0.07)
+    kw = {"bind_to": "image", "no_image_text_loss": True}
+    ref = lo.contrastive_loss_streaming([f.float().numpy() for f in feats], labels.numpy(), float(scale), **kw)
+    mod = cb.ClipLoss(gather_with_grad=True, rank=0, world_size=1, tensor_core_operands="bf16", **kw)
+    loss, grads, ds = _run(mod, [f.to(dev) for f in feats], labels.to(dev), scale.to(dev))
+    assert abs(loss - ref["loss"]) <= 1e-3 * abs(ref["loss"])
+    assert grads[2] is None and ref["grads"][2] is None
+    for i in range(2):
+        assert _rel(grads[i], ref["grads"][i]) < 1e-3 + 2 ** -8, i
     assert abs(ds - ref["dlogit_scale"]) <= 1e-3 * abs(ref["dlogit_scale"])
 
 
