@@ -132,14 +132,17 @@ def _gather_rows(local, labels, gathered, all_labels, group):
     manager.__exit__(None, None, None)
 
 
-def _shard_mode(path, d, group, device):
+_MAX_EXCHANGE_RANKS = 16  # MAX_PEERS of the library (one NVLink domain); larger jobs use the 'local' form
+
+
+def _shard_mode(path, d, group, device, world=2):
     """How a row-sharded step exchanges data:
     'peer'  : S once per pair; all-gather, statistics and the reduce-scatter of the column-side gradients are stores
               into peer-mapped symmetric memory over NVLink (csrc/shard_exchange.cu, loss_grad_gemm.cu);
     'nccl'  : the same step with NCCL collectives (all-gather in, all-reduce of statistics, reduce-scatter out);
     'local' : every rank recomputes S for both of its gradients (two sweeps per pair), NCCL in / all-reduce only.
     CLIBD_SHARD_MODE forces one of them; the default is 'peer' where symmetric memory is available."""
-    exchange_ok = path != _lib.PATH_SIMT_F32 and (d + 63) // 64 * 64 <= 768
+    exchange_ok = path != _lib.PATH_SIMT_F32 and (d + 63) // 64 * 64 <= 768 and world <= _MAX_EXCHANGE_RANKS
     want = os.environ.get("CLIBD_SHARD_MODE", "")
     if want == "local" or not exchange_ok:
         return "local"
@@ -182,7 +185,7 @@ class _FusedClipLossFn(torch.autograd.Function):
         device, dtype = ref.device, ref.dtype
         n, d = ref.shape
         stream = _stream_ptr(device)
-        shard = _shard_mode(path, d, group, device) if world > 1 else "single"
+        shard = _shard_mode(path, d, group, device, world) if world > 1 else "single"
         px = entry = None
         if shard == "peer":
             try:
@@ -494,7 +497,8 @@ class _PeerAllGatherFn(torch.autograd.Function):
 
 
 def _peer_gather_ok(features, world):
-    if world <= 1 or not isinstance(features, torch.Tensor) or not features.is_cuda or features.dim() != 2:
+    if world <= 1 or world > _MAX_EXCHANGE_RANKS or not isinstance(features, torch.Tensor) or not features.is_cuda \
+            or features.dim() != 2:
         return False
     if features.dtype not in _DT or features.shape[0] == 0 or os.environ.get("CLIBD_SHARD_MODE", "") in ("nccl", "local"):
         return False
