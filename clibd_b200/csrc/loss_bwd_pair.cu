@@ -24,6 +24,11 @@
 //     (loss_grad_gemm.cu) instead of a second sweep that recomputes S^T.  Measured at N = 32768: the sweep goes
 //     from 2.65 to ~3.05 ms (the store itself: with the same synchronisation but no store it stays at 2.65, with
 //     the stores aimed at an L2-resident dummy region at 2.86), the GEMM costs 1.17 ms, a second sweep 2.65 ms.
+//     Writing the strip with 16-byte stores from the epilogue's registers instead (no second read of the tile from
+//     shared memory, no store -> wait -> release chain through warp 3) was measured and is slower: 18.55 against
+//     17.21 ms per step, in-process A/B (profiles/r2o2_ab_strip_store_direct_vs_tma.log) -- the epilogue is the
+//     critical path of a tile, and eight more LSU instructions per thread cost more than the TMA's 32 KB of shared-
+//     memory reads.
 //
 // Measured constraints that shaped the code (ncu + clock64 instrumentation, see profiles/):
 //  * shared-memory bandwidth is the ceiling: per 64-cycle MMA a CTA's tensor core reads 2 KB of A and 4 KB of
