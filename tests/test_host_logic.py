@@ -162,3 +162,62 @@ def test_world2_gloo_orchestration_matches_reference_golden(operands):
                 vals, grad = ret[r][f"gather_{with_grad}"]
                 assert np.array_equal(np.asarray(vals, dtype=np.float32), full)
                 assert np.array_equal(np.asarray(grad, dtype=np.float32), np.full((3, 4), gsum, dtype=np.float32))
+
+
+def test_pipeline_bounds_cover_the_key_range():
+    """Block layout of the host-key kNN pipeline (retrieval._pipeline_bounds): contiguous cover of [lo, hi), a small
+    first block, every later block at most twice its predecessor (its copy hides behind the previous block's screen),
+    few blocks; an explicit block count gives equal blocks."""
+    from clibd_b200 import retrieval as R
+    for lo, hi in ((0, 1_000_000), (7, 125_007), (0, 3), (0, 65_537), (100, 100 + (1 << 15)), (0, 5_000_000)):
+        b = R._pipeline_bounds(lo, hi)
+        sizes = [b[i + 1] - b[i] for i in range(len(b) - 1)]
+        assert b[0] == lo and b[-1] == hi and all(s > 0 for s in sizes)
+        assert len(sizes) <= R._PIPELINE_BLOCKS
+        if len(sizes) > 1:
+            assert sizes[0] == R._PIPELINE_FIRST_KEYS
+            assert all(sizes[i + 1] == 2 * sizes[i] for i in range(len(sizes) - 2))  # all but the last: doubling
+            assert sizes[-1] > sizes[-2] or len(sizes) == R._PIPELINE_BLOCKS or sizes[-1] <= 4 * sizes[-2]
+    assert R._pipeline_bounds(0, 10, 4) == [0, 2, 5, 7, 10]
+    assert R._pipeline_bounds(0, 3, 8) == [0, 1, 2, 3]
+
+
+def test_shard_mode_selection(monkeypatch):
+    """Which exchange form a row-sharded step takes (loss._shard_mode): the peer form only on CUDA under NCCL with
+    symmetric memory, for a tensor-core path, d <= 768 and at most 16 ranks; the environment can force a form."""
+    from clibd_b200 import _lib, _peer
+    from clibd_b200 import loss as L
+    cuda = torch.device("cuda", 0)
+    monkeypatch.delenv("CLIBD_SHARD_MODE", raising=False)
+    monkeypatch.setattr(L.dist, "get_backend", lambda group=None: "nccl")
+    monkeypatch.setattr(_peer, "available", lambda: True)
+    assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, cuda, 8) == "peer"
+    assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, cuda, 32) == "local"       # more ranks than peer slots
+    assert L._shard_mode(_lib.PATH_TC_F16, 769, None, cuda, 8) == "local"         # padded d > 768: single-CTA sweep
+    assert L._shard_mode(_lib.PATH_SIMT_F32, 768, None, cuda, 8) == "local"       # exact CUDA-core path
+    assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, torch.device("cpu"), 2) == "nccl"
+    monkeypatch.setattr(_peer, "available", lambda: False)
+    assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, cuda, 8) == "nccl"
+    monkeypatch.setattr(L.dist, "get_backend", lambda group=None: "gloo")
+    monkeypatch.setattr(_peer, "available", lambda: True)
+    assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, cuda, 8) == "nccl"
+    monkeypatch.setattr(L.dist, "get_backend", lambda group=None: "nccl")
+    for forced in ("local", "nccl", "peer"):
+        monkeypatch.setenv("CLIBD_SHARD_MODE", forced)
+        assert L._shard_mode(_lib.PATH_TC_BF16, 768, None, cuda, 8) == forced
+    monkeypatch.setenv("CLIBD_SHARD_MODE", "peer")
+    assert L._shard_mode(_lib.PATH_SIMT_F32, 768, None, cuda, 8) == "local"       # no exchange form for this path
+
+
+def test_peer_disable_is_sticky(monkeypatch):
+    """_peer.disable(reason) (called when mapping the ranks' buffers failed) switches the peer form off for the rest
+    of the process and warns once."""
+    import warnings
+    from clibd_b200 import _peer
+    monkeypatch.setattr(_peer, "_disabled_reason", None)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _peer.disable("no fd passing")
+        _peer.disable("again")
+    assert len(w) == 1 and "no fd passing" in str(w[0].message)
+    assert _peer.available() is False and _peer._disabled_reason == "no fd passing"
