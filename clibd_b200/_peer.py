@@ -39,7 +39,6 @@ except Exception:  # noqa: BLE001  (no distributed build)
     _symm = None
 
 _contexts = {}
-_probe = {}
 
 
 _disabled_reason = None
